@@ -1,0 +1,225 @@
+"""
+oracle/gen_golden.py -- generate tests/golden/*.npz from the LIVE reference.  TEST INFRASTRUCTURE.
+
+Runs only in the authoring container, where the unmodified reference is mounted read-only at
+/root/reference (Python + Numba; it cannot travel to the GPU box, hence committed fixtures):
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.gen_golden
+
+What is produced (all from the reference's own functions, reference: src/ml2048/game_numba.py):
+
+  kat_playground.npz   the one known-answer vector the reference holds (playground.ipynb:3915-3926,
+                       printed output :3901-3906), re-run through the live reference here
+  line_table.npz       exhaustive 18^4 lines x {toward cell 0, toward cell 3}: pushed line, fused
+                       exponents (_push_row :48-90) and the movable flags (_line_movable :215-256)
+  boards.npz           random boards x 4 actions: moved board, merged, mask, the four rewards
+  rollout_*.npz        lock-step rollouts through VecGame (prepare/observations/step), every
+                       VecStepResult field + ids + reset indices (full or CRC32 digests)
+  schedule_*.npz       the host random draws of one rollout recorded from the reference's generator
+                       (tables at every refresh, coins, offsets): input of the "replay" mode
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+REF_SRC = "/root/reference/src"
+sys.path.insert(0, REF_SRC)
+
+import numba  # noqa: E402
+from ml2048 import game_numba as ref  # noqa: E402
+
+from .rollout import record_rollout  # noqa: E402
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+REWARDS = {
+    "normal": ref.reward_fn_normal,
+    "improved": ref.reward_fn_improved,
+    "rank": ref.reward_fn_rank,
+    "maxcell": ref.reward_fn_maxcell,
+}
+
+# (name, M, N, env seed, reward, two_prob, action seed, wild fraction, keep full arrays)
+ROLLOUTS = [
+    ("c1_seed0_normal", 1024, 64, 0, "normal", 0.8, 7, 0.05, True),     # BASELINE config 1
+    ("c1_seed1_improved", 1024, 64, 1, "improved", 0.8, 7, 0.05, False),
+    ("c1_seed123_normal", 1024, 64, 123, "normal", 0.8, 7, 0.0, False),
+    ("ragged_rank", 1500, 300, 5, "rank", 0.8, 11, 0.05, False),          # M not a multiple of 1024, many resets
+    ("twoprob_maxcell", 2304, 200, 9, "maxcell", 0.5, 13, 0.10, False),   # M > 1024: table-row aliasing
+    ("tiny_long", 7, 1500, 3, "improved", 0.8, 17, 0.02, False),          # many refreshes, tiny M
+    ("train_shape", 2048, 64, 2024, "improved", 0.8, 19, 0.0, False),     # BASELINE config 2
+    ("one_game", 1, 400, 4, "normal", 0.8, 23, 0.05, False),
+]
+
+SCHEDULES = [("sched_small", 96, 80, 42, "improved", 0.8, 29, 0.05)]
+
+
+class _RecordingGenerator:
+    """Wraps the reference instance's numpy Generator and logs what VecGame draws from it."""
+
+    def __init__(self, inner: np.random.Generator):
+        self._inner = inner
+        self.coins: list[float] = []
+        self.offsets: list[int] = []
+        self.perms: list[np.ndarray] = []
+        self.floats: list[np.ndarray] = []
+
+    def random(self, *args, **kwargs):
+        r = self._inner.random(*args, **kwargs)
+        if "out" in kwargs:
+            self.floats.append(np.array(kwargs["out"], copy=True))
+        else:
+            self.coins.append(float(r))
+        return r
+
+    def integers(self, *args, **kwargs):
+        r = self._inner.integers(*args, **kwargs)
+        self.offsets.append(int(r))
+        return r
+
+    def permuted(self, *args, **kwargs):
+        r = self._inner.permuted(*args, **kwargs)
+        self.perms.append(np.array(kwargs["out"], copy=True))
+        return r
+
+
+@numba.njit
+def _lines_via_reference(lines, toward_last, out_lines, out_buckets, out_f, out_b):
+    n = lines.shape[0]
+    for i in range(n):
+        row = lines[i].copy()
+        buckets = np.zeros(18, dtype=np.uint8)
+        if toward_last:
+            ref._push_row(row, 3, -1, buckets)
+        else:
+            ref._push_row(row, 0, 1, buckets)
+        out_lines[i, :] = row
+        out_buckets[i, :] = buckets
+        f, b = ref._line_movable(lines[i, 0], lines[i, 1], lines[i, 2], lines[i, 3])
+        out_f[i] = f
+        out_b[i] = b
+
+
+def gen_kat() -> None:
+    # playground.ipynb:3915-3926
+    np.random.seed(12322)
+    state = np.random.randint(8, 11, (16,), dtype=np.int8)
+    prev = state.copy()
+    merged = np.zeros_like(state)
+    ref._step_left(state, merged)
+    rn = ref.reward_fn_normal(state, prev, merged)
+    rr = ref.reward_fn_rank(state, prev, merged)
+    rm = ref.reward_fn_maxcell(state, prev, merged)
+    # the printed output of the notebook, :3901-3906
+    assert prev.tolist() == [10, 10, 8, 10, 10, 9, 8, 10, 9, 10, 9, 9, 10, 10, 9, 9]
+    assert state.tolist() == [11, 8, 10, 0, 10, 9, 8, 10, 9, 10, 10, 0, 11, 10, 0, 0]
+    assert (rn, rr, rm) == (6144.0, 42.0, 2052.0)
+    np.savez_compressed(os.path.join(OUT_DIR, "kat_playground.npz"), prev=prev, state=state, merged=merged,
+                        reward_normal=rn, reward_rank=rr, reward_maxcell=rm)
+
+
+def gen_line_table() -> None:
+    v = np.arange(18, dtype=np.uint8)
+    lines = np.stack(np.meshgrid(v, v, v, v, indexing="ij"), axis=-1).reshape(-1, 4)
+    n = lines.shape[0]
+    res = {}
+    for name, toward_last in (("first", False), ("last", True)):
+        out_lines = np.zeros((n, 4), np.uint8)
+        out_buckets = np.zeros((n, 18), np.uint8)
+        f = np.zeros(n, np.bool_)
+        b = np.zeros(n, np.bool_)
+        _lines_via_reference(lines, toward_last, out_lines, out_buckets, f, b)
+        res[f"pushed_{name}"] = out_lines
+        # at most two fusions per line: store the fused exponents (0 = none), ascending
+        fused = np.zeros((n, 2), np.uint8)
+        for i in np.flatnonzero(out_buckets.sum(axis=1)):
+            ks = np.repeat(np.arange(18), out_buckets[i])
+            fused[i, : ks.size] = ks
+        res[f"fused_{name}"] = fused
+        res["movable_first"] = f
+        res["movable_last"] = b
+    np.savez_compressed(os.path.join(OUT_DIR, "line_table.npz"), **res)
+
+
+def gen_boards() -> None:
+    rng = np.random.default_rng(20481)
+    n = 4096
+    # mixture: sparse early boards, dense late boards, boards with large exponents, dead boards
+    dens = rng.choice([0.2, 0.5, 0.8, 1.0], size=n)
+    hi = rng.choice([3, 6, 11, 15], size=n)  # fusing exponent >= 16 would index merged[16+] (out of bounds in the reference)
+    boards = (rng.integers(1, 18, size=(n, 16)) % hi[:, None] + 1).astype(np.uint8)
+    boards[rng.random((n, 16)) >= dens[:, None]] = 0
+    boards[0] = 0
+    boards[1] = np.array([1, 2, 1, 2, 2, 1, 2, 1, 1, 2, 1, 2, 2, 1, 2, 1], np.uint8)  # dead board
+    boards[2] = 15
+    moved = np.zeros((n, 4, 16), np.uint8)
+    merged = np.zeros((n, 4, 16), np.uint8)
+    mask = np.zeros((n, 4), np.uint8)
+    rewards = np.zeros((n, 4, 4), np.float64)
+    for i in range(n):
+        ref._compute_valid_actions(boards[i], mask[i])
+        for a in range(4):
+            b = boards[i].copy()
+            m = np.zeros(16, np.uint8)
+            ref._step_kernel(b, m, a)
+            moved[i, a] = b
+            merged[i, a] = m
+            for j, fn in enumerate(REWARDS.values()):
+                rewards[i, a, j] = fn(b, boards[i], m)
+    np.savez_compressed(os.path.join(OUT_DIR, "boards.npz"), boards=boards, moved=moved, merged=merged, mask=mask,
+                        rewards=rewards, reward_names=np.array(list(REWARDS)))
+
+
+def gen_rollouts() -> None:
+    for name, m, n, seed, reward, two_prob, aseed, wild, full in ROLLOUTS:
+        vg = ref.VecGame(m, REWARDS[reward], two_prob=two_prob)
+        vg.reset(seed)
+        rec = record_rollout(vg, n, action_seed=aseed, wild=wild, full=full)
+        rec["meta"] = np.array([m, n, seed, aseed], dtype=np.int64)
+        rec["meta_f"] = np.array([two_prob, wild], dtype=np.float64)
+        rec["reward_kind"] = np.array(reward)
+        np.savez_compressed(os.path.join(OUT_DIR, f"rollout_{name}.npz"), **rec)
+        print(f"rollout {name}: resets={int(rec['n_reset'].sum())} games={int(rec['final_game_count'])}")
+
+
+def gen_schedules() -> None:
+    for name, m, n, seed, reward, two_prob, aseed, wild in SCHEDULES:
+        vg = ref.VecGame(m, REWARDS[reward], two_prob=two_prob)
+        vg.reset(seed)
+        first_perm, first_float = vg._randperm.copy(), vg._randfloat.copy()
+        proxy = _RecordingGenerator(vg._rand)
+        vg._rand = proxy
+        rec = record_rollout(vg, n, action_seed=aseed, wild=wild, full=True)
+        rec["meta"] = np.array([m, n, seed, aseed], dtype=np.int64)
+        rec["meta_f"] = np.array([two_prob, wild], dtype=np.float64)
+        rec["reward_kind"] = np.array(reward)
+        rec["sched_coins"] = np.asarray(proxy.coins, np.float64)
+        rec["sched_offsets"] = np.asarray(proxy.offsets, np.int64)
+        rec["sched_perms"] = np.stack([first_perm] + proxy.perms)
+        # only randfloat[0:16] is ever read (game_numba.py:207); keep the whole row anyway
+        rec["sched_floats"] = np.stack([first_float] + proxy.floats)
+        np.savez_compressed(os.path.join(OUT_DIR, f"schedule_{name}.npz"), **rec)
+        print(f"schedule {name}: refreshes={len(proxy.perms)}")
+
+
+def main() -> None:
+    os.makedirs(OUT_DIR, exist_ok=True)
+    print("numba", numba.__version__, "numpy", np.__version__)
+    only = set(sys.argv[1:])
+    for name, fn in (("kat", gen_kat), ("lines", gen_line_table), ("boards", gen_boards), ("rollouts", gen_rollouts),
+                     ("schedules", gen_schedules)):
+        if not only or name in only:
+            fn()
+    with open(os.path.join(OUT_DIR, "PROVENANCE.txt"), "w") as fh:
+        fh.write("generated by oracle/gen_golden.py from the live reference at /root/reference/src\n")
+        fh.write(f"numba {numba.__version__} numpy {np.__version__} python {sys.version.split()[0]}\n")
+
+
+if __name__ == "__main__":
+    main()
