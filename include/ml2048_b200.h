@@ -1,0 +1,203 @@
+/*
+ * ml2048_b200.h -- C ABI of the B200-native VecGame hot path (libml2048_b200.so).
+ *
+ * The reference (tsangwpx/ml2048) has no FFI layer: its boundary for this path is the Python class
+ * `VecGame` plus the Numba-jitted functions it calls (reference: src/ml2048/game_numba.py).  Every
+ * entry point below replaces one of those jitted functions / host loops; the citation says which.
+ * The Python shim `ml2048_b200.VecGame` keeps the reference's class surface and calls these through
+ * ctypes (see INTEGRATION.md for the binding a maintainer would add on the reference side).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the library never allocates, frees or retains memory;  all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*) and the call returns immediately: no hidden synchronisation,
+ *     CUDA-graph capturable;
+ *   - return value: 0 = ok, negative = argument error (ML2048_E_*), positive = cudaError_t of the launch;
+ *   - boards are 16 bytes per game (exponents, 0 = empty, cell = row*4+col, game_numba.py:13-20),
+ *     16-byte aligned;  masks are 4 bytes per game (left,right,up,down; game.py:14-17), 4-byte aligned;
+ *   - "slot" = index of a game inside this shard; global slot = slot_base + slot (multi-GPU sharding:
+ *     table rows and Philox counters use the GLOBAL slot so results do not depend on the shard count).
+ */
+#ifndef ML2048_B200_H
+#define ML2048_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ML2048_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ML2048_API __attribute__((visibility("default")))
+#else
+#define ML2048_API
+#endif
+
+/* error codes (negative) */
+#define ML2048_E_NULL (-1)    /* required pointer is null */
+#define ML2048_E_ALIGN (-2)   /* pointer not aligned as documented */
+#define ML2048_E_SIZE (-3)    /* num_games <= 0 or capacity too small */
+#define ML2048_E_ENUM (-4)    /* bad enum value */
+#define ML2048_E_STRUCT (-5)  /* struct_size does not match this library */
+
+/* reward_fn, selected by identity on the Python side (game_numba.py:408-504) */
+enum { ML2048_REWARD_NORMAL = 0, ML2048_REWARD_IMPROVED = 1, ML2048_REWARD_RANK = 2, ML2048_REWARD_MAXCELL = 3 };
+
+/* where spawn randomness comes from */
+enum {
+    ML2048_RNG_REPLAY = 0, /* the reference's pre-drawn tables: bit-exact (game_numba.py:172-212) */
+    ML2048_RNG_PHILOX = 1  /* counter-based Philox4x32-10 keyed by (seed, global slot, step counter) */
+};
+
+/* element type of the `actions` array */
+enum { ML2048_ACT_U8 = 0, ML2048_ACT_I32 = 1, ML2048_ACT_I64 = 2 };
+
+/* where actions come from */
+enum {
+    ML2048_ACTIONS_GIVEN = 0,       /* read `actions` */
+    ML2048_ACTIONS_RANDOM_VALID = 1 /* uniform over valid actions, Philox (policy/random.py:17-27);
+                                       the chosen action is written to `actions_out` when not null */
+};
+
+/* fused observation encoding (policy/_network.py:86-95): out[g][k][c] = (board[g][c] == k), k < 16 */
+enum { ML2048_ONEHOT_NONE = 0, ML2048_ONEHOT_F32 = 1, ML2048_ONEHOT_BF16 = 2, ML2048_ONEHOT_U8 = 3 };
+
+/* Episode statistics accumulated on the device (RunnerStats, runner.py:139-189, plus score/step moments).
+ * `replicas` copies of this struct are laid out back to back to spread atomics; sum them to read. */
+typedef struct {
+    unsigned long long max_tile_hist[20]; /* runner.py:150-166: counts[max exponent] of finished games */
+    unsigned long long episodes;          /* runner.py:166 terminated_count */
+    unsigned long long score_sum;         /* sum of final scores (scores are integers) */
+    unsigned long long step_sum;          /* sum of final step counts */
+    unsigned long long score_max;         /* max final score */
+} ml2048_stats;
+
+#define ML2048_STATS_REPLICAS 64
+
+/* Arguments of one environment step.  Replaces VecGame.step + _vec_step
+ * (game_numba.py:660-698, 701-738) including the prev_state / prev_valid_actions copies (:672-673):
+ * boards and masks are ping-pong buffers, so board_in / valid_in ARE the "prev" arrays afterwards. */
+typedef struct {
+    uint32_t struct_size;  /* sizeof(ml2048_step_args) */
+    int32_t reward_kind;   /* ML2048_REWARD_* */
+    int32_t rng_mode;      /* ML2048_RNG_* */
+    int32_t action_dtype;  /* ML2048_ACT_* */
+    int32_t action_mode;   /* ML2048_ACTIONS_* */
+    int32_t onehot_dtype;  /* ML2048_ONEHOT_* */
+    int64_t num_games;     /* games in this shard */
+    int64_t slot_base;     /* global slot of game 0 of this shard */
+
+    const void *board_in;  /* [num_games][16] u8 */
+    void *board_out;       /* [num_games][16] u8, must not alias board_in */
+    const void *valid_in;  /* [num_games][4] u8; only read when action_mode == RANDOM_VALID, else may be null */
+    void *valid_out;       /* [num_games][4] u8 */
+    const void *actions;   /* [num_games] of action_dtype, values 0..3 (others count as invalid moves) */
+    void *actions_out;     /* [num_games] u8 or null (RANDOM_VALID only) */
+
+    int32_t *step;         /* in place; += 1 on a valid move            (game_numba.py:719) */
+    float *score;          /* in place; += normal reward on a valid move (:729-731) */
+    float *reward;         /* in place; written on a valid move only: stays stale otherwise (:730, :737-738) */
+    uint8_t *terminated;   /* in place; written on a valid move only (:735) */
+    uint8_t *invalid;      /* always written (:736, :738) */
+    uint8_t *merged;       /* [num_games][16] or null; written on a valid move only (:723) */
+
+    void *onehot_out;      /* [num_games][16][16] of onehot_dtype, or null */
+
+    /* replay mode (game_numba.py:733, 172-212) */
+    const uint8_t *randperm; /* [1024][16] permutations of 0..15 */
+    int64_t rand_seed;       /* _rand_step + rand_offset (:681); row = (rand_seed + global slot) mod 1024 */
+    uint32_t two_mask;       /* bit c set <=> (double)randfloat[c] < two_prob (see ml2048_two_mask) */
+
+    /* philox mode */
+    uint32_t two_threshold;  /* spawn a 2 iff philox word < two_threshold (see ml2048_two_threshold) */
+    uint64_t philox_seed;
+    uint64_t philox_counter; /* caller increments once per step */
+
+    ml2048_stats *stats;     /* [ML2048_STATS_REPLICAS] or null: finished-episode statistics */
+} ml2048_step_args;
+
+/* Arguments of the auto-reset.  Replaces the host loop of VecGame.prepare (game_numba.py:629-658):
+ * every terminated slot, in ascending slot order, is cleared, gets the next id, two spawned tiles and
+ * a mask.  Works in place on the CURRENT boards/masks. */
+typedef struct {
+    uint32_t struct_size;
+    int32_t rng_mode;
+    int32_t onehot_dtype;
+    int32_t reserved0;
+    int64_t num_games;
+    int64_t slot_base;
+
+    void *board;           /* [num_games][16] */
+    void *valid;           /* [num_games][4] */
+    int32_t *id;           /* [num_games] (game_numba.py:641-644) */
+    int32_t *step;
+    float *score;
+    float *reward;
+    uint8_t *terminated;   /* [ceil16(num_games)] : padded to a multiple of 16 bytes, padding zero */
+    uint8_t *invalid;
+    uint8_t *merged;       /* or null */
+    void *onehot;          /* or null: rows of reset games are rewritten */
+
+    const uint8_t *randperm;
+    int64_t rand_base;     /* _rand_step + rand_offset (:651) */
+    uint32_t two_mask;
+    uint32_t two_threshold;
+    uint64_t philox_seed;
+    uint64_t philox_counter;
+
+    int64_t *game_count;   /* device scalar: next id; advanced by the number of resets (:641-642).
+                              With id_offset != null (multi-GPU global ids) it is NOT advanced here. */
+    const int64_t *id_offset; /* or null: device scalar added to ids of this shard (exclusive scan over ranks) */
+    int64_t *reset_count;  /* device scalar out: number of slots reset by this call */
+    int64_t *reset_indices;/* [num_games] out, ascending slots (np.flatnonzero, :629), or null */
+    int32_t *scratch;      /* [ml2048_prepare_scratch_ints(num_games)] */
+} ml2048_prepare_args;
+
+/* ---- entry points ---------------------------------------------------------------------------- */
+
+ML2048_API int ml2048_abi_version(void);
+
+/* ints of scratch ml2048_prepare needs for num_games */
+ML2048_API int64_t ml2048_prepare_scratch_ints(int64_t num_games);
+
+/* _vec_step + VecGame.step body: game_numba.py:660-738 */
+ML2048_API int ml2048_step(const ml2048_step_args *args, void *stream);
+
+/* VecGame.prepare reset loop: game_numba.py:629-658.  ml2048_prepare = count + apply.  The two halves
+ * are exported so a multi-GPU caller can exchange per-rank reset counts between them (all_gather of
+ * *reset_count -> id_offset) and keep ids globally slot-ordered like the single-process reference:
+ *   count: np.flatnonzero(terminated) bookkeeping (:629) -> *reset_count, slot-ordered offsets in scratch
+ *   apply: the per-slot reset body (:634-656) */
+ML2048_API int ml2048_prepare(const ml2048_prepare_args *args, void *stream);
+ML2048_API int ml2048_prepare_count(const ml2048_prepare_args *args, void *stream);
+ML2048_API int ml2048_prepare_apply(const ml2048_prepare_args *args, void *stream);
+
+/* VecGame.reset data part (game_numba.py:613-617): zero all per-game state, mark every game terminated */
+ML2048_API int ml2048_reset_state(void *board_a, void *board_b, void *valid_a, void *valid_b, int32_t *id, int32_t *step, float *score,
+                       float *reward, uint8_t *terminated, uint8_t *invalid, uint8_t *merged, int64_t num_games, void *stream);
+
+/* CNNEncoder.forward input encoding as a stand-alone op: policy/_network.py:86-95 */
+ML2048_API int ml2048_encode_onehot(const void *board, void *out, int32_t onehot_dtype, int64_t num_games, void *stream);
+
+/* _compute_valid_actions over a batch: game_numba.py:259-289 */
+ML2048_API int ml2048_valid_actions(const void *board, void *valid_out, int64_t num_games, void *stream);
+
+/* _update_count (runner.py:120-136): hist[max exponent] += 1 for every game with terminated != 0;
+ * with terminated == null: VecGame.summary's histogram over all live boards (game_numba.py:593-596).
+ * hist20 is [20] unsigned long long, accumulated (not cleared). */
+ML2048_API int ml2048_max_tile_hist(const void *board, const uint8_t *terminated, int64_t num_games, unsigned long long *hist20, void *stream);
+
+/* uniform-over-valid action sampler (policy/random.py:17-27) as a stand-alone op */
+ML2048_API int ml2048_sample_random_valid(const void *valid, uint8_t *actions_out, int64_t num_games, int64_t slot_base,
+                               uint64_t philox_seed, uint64_t philox_counter, void *stream);
+
+/* host helpers (no GPU work) */
+ML2048_API uint32_t ml2048_two_mask(const float *host_randfloat16, double two_prob);   /* game_numba.py:207 (f32 -> f64 compare) */
+ML2048_API uint32_t ml2048_two_threshold(double two_prob);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ML2048_B200_H */

@@ -1,0 +1,145 @@
+"""ctypes binding of libml2048_b200.so (the C ABI declared in include/ml2048_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or cannot be loaded the import of the
+environment fails loudly.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libml2048_b200.so")
+
+ABI_VERSION = 1
+STATS_REPLICAS = 64
+STATS_WORDS = 24  # 20 histogram bins + episodes, score_sum, step_sum, score_max (unsigned long long each)
+
+REWARD_NORMAL, REWARD_IMPROVED, REWARD_RANK, REWARD_MAXCELL = 0, 1, 2, 3
+RNG_REPLAY, RNG_PHILOX = 0, 1
+ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
+ACTIONS_GIVEN, ACTIONS_RANDOM_VALID = 0, 1
+ONEHOT_NONE, ONEHOT_F32, ONEHOT_BF16, ONEHOT_U8 = 0, 1, 2, 3
+
+ERRORS = {-1: "null pointer", -2: "misaligned pointer", -3: "bad size", -4: "bad enum", -5: "struct size mismatch"}
+
+
+class StepArgs(C.Structure):
+    """ml2048_step_args"""
+
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("reward_kind", C.c_int32),
+        ("rng_mode", C.c_int32),
+        ("action_dtype", C.c_int32),
+        ("action_mode", C.c_int32),
+        ("onehot_dtype", C.c_int32),
+        ("num_games", C.c_int64),
+        ("slot_base", C.c_int64),
+        ("board_in", C.c_void_p),
+        ("board_out", C.c_void_p),
+        ("valid_in", C.c_void_p),
+        ("valid_out", C.c_void_p),
+        ("actions", C.c_void_p),
+        ("actions_out", C.c_void_p),
+        ("step", C.c_void_p),
+        ("score", C.c_void_p),
+        ("reward", C.c_void_p),
+        ("terminated", C.c_void_p),
+        ("invalid", C.c_void_p),
+        ("merged", C.c_void_p),
+        ("onehot_out", C.c_void_p),
+        ("randperm", C.c_void_p),
+        ("rand_seed", C.c_int64),
+        ("two_mask", C.c_uint32),
+        ("two_threshold", C.c_uint32),
+        ("philox_seed", C.c_uint64),
+        ("philox_counter", C.c_uint64),
+        ("stats", C.c_void_p),
+    ]
+
+
+class PrepareArgs(C.Structure):
+    """ml2048_prepare_args"""
+
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("rng_mode", C.c_int32),
+        ("onehot_dtype", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("num_games", C.c_int64),
+        ("slot_base", C.c_int64),
+        ("board", C.c_void_p),
+        ("valid", C.c_void_p),
+        ("id", C.c_void_p),
+        ("step", C.c_void_p),
+        ("score", C.c_void_p),
+        ("reward", C.c_void_p),
+        ("terminated", C.c_void_p),
+        ("invalid", C.c_void_p),
+        ("merged", C.c_void_p),
+        ("onehot", C.c_void_p),
+        ("randperm", C.c_void_p),
+        ("rand_base", C.c_int64),
+        ("two_mask", C.c_uint32),
+        ("two_threshold", C.c_uint32),
+        ("philox_seed", C.c_uint64),
+        ("philox_counter", C.c_uint64),
+        ("game_count", C.c_void_p),
+        ("id_offset", C.c_void_p),
+        ("reset_count", C.c_void_p),
+        ("reset_indices", C.c_void_p),
+        ("scratch", C.c_void_p),
+    ]
+
+
+# every symbol include/ml2048_b200.h declares: (name, restype, argtypes)
+_VP, _I64, _I32, _U64, _U32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32
+SYMBOLS = {
+    "ml2048_abi_version": (C.c_int, []),
+    "ml2048_prepare_scratch_ints": (_I64, [_I64]),
+    "ml2048_step": (C.c_int, [C.POINTER(StepArgs), _VP]),
+    "ml2048_prepare": (C.c_int, [C.POINTER(PrepareArgs), _VP]),
+    "ml2048_prepare_count": (C.c_int, [C.POINTER(PrepareArgs), _VP]),
+    "ml2048_prepare_apply": (C.c_int, [C.POINTER(PrepareArgs), _VP]),
+    "ml2048_reset_state": (C.c_int, [_VP] * 11 + [_I64, _VP]),
+    "ml2048_encode_onehot": (C.c_int, [_VP, _VP, _I32, _I64, _VP]),
+    "ml2048_valid_actions": (C.c_int, [_VP, _VP, _I64, _VP]),
+    "ml2048_max_tile_hist": (C.c_int, [_VP, _VP, _I64, _VP, _VP]),
+    "ml2048_sample_random_valid": (C.c_int, [_VP, _VP, _I64, _I64, _U64, _U64, _VP]),
+    "ml2048_two_mask": (_U32, [_VP, C.c_double]),
+    "ml2048_two_threshold": (_U32, [C.c_double]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m ml2048_b200.build` (nvcc, sm_100a). "
+            "ml2048_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    got = lib.ml2048_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError(f"libml2048_b200.so ABI {got} != expected {ABI_VERSION}: rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError(f"{what}: argument error {rc} ({ERRORS.get(rc, '?')})")
+    raise RuntimeError(f"{what}: CUDA error {rc}")

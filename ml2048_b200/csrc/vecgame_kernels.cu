@@ -1,0 +1,675 @@
+// vecgame_kernels.cu -- sm_100a kernels + C ABI for the VecGame hot path (see include/ml2048_b200.h).
+//
+// Layout in HBM (struct-of-arrays, one entry per game, all owned by the caller):
+//   board[2]   uint4   ping-pong: step reads one, writes the other => prev_state costs nothing
+//   valid[2]   uint32  ping-pong (left,right,up,down bytes)       => prev_valid_actions costs nothing
+//   step i32, score f32, reward f32, terminated u8, invalid u8, id i32, merged uint4 (optional)
+// One thread owns one game; a warp's 32 games are contiguous in every array, so every load/store is a
+// fully coalesced 32 B..512 B access.  The fused one-hot observation (1 KiB per game in fp32) is
+// written cooperatively by the whole block from boards staged in shared memory so that each warp
+// store instruction covers 512 contiguous bytes.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/ml2048_b200.h"
+#include "board_ops.cuh"
+
+using namespace ml2048;
+
+namespace {
+
+constexpr int kStepThreads = 256;   // games per block in the step kernel
+constexpr int kPrepThreads = 256;   // threads per block in the auto-reset kernels
+constexpr int kPrepTile = kPrepThreads * 16;  // games per block there (16 terminated flags per thread)
+constexpr int kRandRows = 1024;     // VecGame._RAND_SIZE, game_numba.py:533
+
+// ---- streaming access helpers ---------------------------------------------------------------
+
+__device__ __forceinline__ void store_streaming(float4 *p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void store_streaming(uint4 *p, uint4 v) { __stcs(p, v); }
+
+// ---- one-hot tile writer --------------------------------------------------------------------
+// out[g][k][c] = (board[g][c] == k) for k < 16 (policy/_network.py:86-95: one_hot(x,16).float().permute(0,2,1)).
+// The block's boards sit in shared memory; thread t owns the fixed (class k, column group q) pair
+// t mod 64 and walks the games, so one warp instruction stores 32 consecutive 16-byte pieces.
+
+template <int kDtype>
+struct OneHotPiece;
+
+template <>
+struct OneHotPiece<ML2048_ONEHOT_F32> {  // 4 cells -> 4 floats = 16 bytes; 64 pieces per game
+    using vec = float4;
+    static constexpr int kPiecesPerGame = 64;
+    static __device__ __forceinline__ vec make(const uint4 *boards, int game, int piece)
+    {
+        const uint32_t k = (uint32_t)piece >> 2;
+        const uint32_t word = reinterpret_cast<const uint32_t *>(boards + game)[piece & 3];
+        const uint32_t eq = (((word ^ (k * 0x01010101u)) + kLo7) & kHi) ^ kHi;  // 0x80 where cell == k
+        float4 v;
+        v.x = __uint_as_float(prmt(eq, 0u, 0x8888) & 0x3f800000u);
+        v.y = __uint_as_float(prmt(eq, 0u, 0x9999) & 0x3f800000u);
+        v.z = __uint_as_float(prmt(eq, 0u, 0xaaaa) & 0x3f800000u);
+        v.w = __uint_as_float(prmt(eq, 0u, 0xbbbb) & 0x3f800000u);
+        return v;
+    }
+};
+
+template <>
+struct OneHotPiece<ML2048_ONEHOT_BF16> {  // 8 cells -> 8 bf16 = 16 bytes; 32 pieces per game
+    using vec = uint4;
+    static constexpr int kPiecesPerGame = 32;
+    static __device__ __forceinline__ uint32_t pair(uint32_t eq, uint32_t sel)
+    {
+        return prmt(eq, 0u, sel) & 0x3f803f80u;  // two bf16 1.0 (0x3f80) where the cells matched
+    }
+    static __device__ __forceinline__ vec make(const uint4 *boards, int game, int piece)
+    {
+        const uint32_t k = (uint32_t)piece >> 1;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(boards + game) + (piece & 1) * 2;
+        const uint32_t kk = k * 0x01010101u;
+        const uint32_t e0 = (((w[0] ^ kk) + kLo7) & kHi) ^ kHi;
+        const uint32_t e1 = (((w[1] ^ kk) + kLo7) & kHi) ^ kHi;
+        return make_uint4(pair(e0, 0x9988), pair(e0, 0xbbaa), pair(e1, 0x9988), pair(e1, 0xbbaa));
+    }
+};
+
+template <>
+struct OneHotPiece<ML2048_ONEHOT_U8> {  // 16 cells -> 16 bytes; 16 pieces per game
+    using vec = uint4;
+    static constexpr int kPiecesPerGame = 16;
+    static __device__ __forceinline__ vec make(const uint4 *boards, int game, int piece)
+    {
+        const uint4 b = boards[game];
+        const uint32_t kk = (uint32_t)piece * 0x01010101u;
+        return make_uint4(((((b.x ^ kk) + kLo7) & kHi) ^ kHi) >> 7, ((((b.y ^ kk) + kLo7) & kHi) ^ kHi) >> 7,
+                          ((((b.z ^ kk) + kLo7) & kHi) ^ kHi) >> 7, ((((b.w ^ kk) + kLo7) & kHi) ^ kHi) >> 7);
+    }
+};
+
+// Emit the one-hot rows of `games` consecutive games whose boards are in shared memory.
+template <int kDtype, int kThreads>
+__device__ __forceinline__ void write_onehot_tile(const uint4 *sboards, int games, void *out_base, int64_t first_game)
+{
+    using P = OneHotPiece<kDtype>;
+    constexpr int kPer = P::kPiecesPerGame;
+    static_assert(kThreads % kPer == 0, "block size must be a multiple of the pieces per game");
+    constexpr int kGamesPerPass = kThreads / kPer;
+    typename P::vec *out = reinterpret_cast<typename P::vec *>(out_base) + first_game * kPer;
+    const int piece = threadIdx.x % kPer;
+    const int g0 = threadIdx.x / kPer;
+#pragma unroll 4
+    for (int g = g0; g < games; g += kGamesPerPass)
+        store_streaming(out + (int64_t)g * kPer + piece, P::make(sboards, g, piece));
+}
+
+// One game's one-hot row written by a single thread (reset path: rare, so no cooperation needed).
+template <int kDtype>
+__device__ __forceinline__ void write_onehot_single(uint4 board, void *out_base, int64_t game)
+{
+    using P = OneHotPiece<kDtype>;
+    typename P::vec *out = reinterpret_cast<typename P::vec *>(out_base) + game * P::kPiecesPerGame;
+    for (int piece = 0; piece < P::kPiecesPerGame; ++piece)
+        out[piece] = P::make(&board, 0, piece);
+}
+
+__device__ __forceinline__ void write_onehot_single_dyn(int dtype, uint4 board, void *out_base, int64_t game)
+{
+    if (dtype == ML2048_ONEHOT_F32) write_onehot_single<ML2048_ONEHOT_F32>(board, out_base, game);
+    else if (dtype == ML2048_ONEHOT_BF16) write_onehot_single<ML2048_ONEHOT_BF16>(board, out_base, game);
+    else if (dtype == ML2048_ONEHOT_U8) write_onehot_single<ML2048_ONEHOT_U8>(board, out_base, game);
+}
+
+// ---- the step kernel ------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, int64_t g)
+{
+    if (dtype == ML2048_ACT_U8) return reinterpret_cast<const uint8_t *>(actions)[g];
+    if (dtype == ML2048_ACT_I32) return (uint32_t) reinterpret_cast<const int32_t *>(actions)[g];
+    const long long a = reinterpret_cast<const long long *>(actions)[g];
+    return (a < 0 || a > 3) ? 4u : (uint32_t)a;
+}
+
+// Replaces _vec_step (game_numba.py:701-738) + the prev copies of VecGame.step (:672-673).
+template <int kRng, bool kLog, int kOneHot>
+__global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_args a)
+{
+    __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kStepThreads : 1];
+    const int64_t block_first = (int64_t)blockIdx.x * kStepThreads;
+    const int64_t g = block_first + threadIdx.x;
+    const bool live = g < a.num_games;
+    uint4 out_board = make_uint4(0, 0, 0, 0);
+
+    if (live) {
+        const uint4 bd = reinterpret_cast<const uint4 *>(a.board_in)[g];
+        const uint64_t slot = (uint64_t)(a.slot_base + g);
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        if (kRng == ML2048_RNG_PHILOX || a.action_mode == ML2048_ACTIONS_RANDOM_VALID)
+            rnd = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)a.philox_counter,
+                                           (uint32_t)(a.philox_counter >> 32)),
+                                make_uint2((uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32)));
+        uint32_t action;
+        if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
+            // uniform over the valid directions (policy/random.py:17-27); 0 when the game is over
+            const uint32_t vm = reinterpret_cast<const uint32_t *>(a.valid_in)[g];
+            const uint32_t bits = (vm & 1u) | ((vm >> 7) & 2u) | ((vm >> 14) & 4u) | ((vm >> 21) & 8u);
+            const uint32_t nv = __popc(bits);
+            action = nv ? kth_set_bit16(bits, __umulhi(rnd.z, nv)) : 0u;
+            if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
+        } else {
+            action = load_action(a.actions, a.action_dtype, g);
+        }
+
+        uint32_t r0 = bd.x, r1 = bd.y, r2 = bd.z, r3 = bd.w;
+        Fusions f = {0u, 0u, 0u, 0ull};
+        move_board<kLog>(r0, r1, r2, r3, action & 3u, f);
+        // valid_actions[action] (game_numba.py:718) == "the move changes the board"; out-of-range
+        // actions (which the reference would index out of bounds with) count as invalid moves
+        const bool moved = (action < 4u) && (((r0 ^ bd.x) | (r1 ^ bd.y) | (r2 ^ bd.z) | (r3 ^ bd.w)) != 0u);
+
+        if (moved) {
+            // reward_fn (:728) and the score increment (:729-731)
+            float reward;
+            if (a.reward_kind == ML2048_REWARD_IMPROVED) {
+                // potential shaping on cell 0, game_numba.py:455-466 (all terms are exact integers in f32)
+                const uint32_t s0 = r0 & 0xffu, p0 = bd.x & 0xffu;
+                const int extra = (s0 ? (64 << s0) : 0) - (p0 ? (64 << p0) : 0);
+                reward = (float)((int)f.gain + extra);
+            } else if (a.reward_kind == ML2048_REWARD_RANK) {
+                reward = (float)f.rank;
+            } else if (a.reward_kind == ML2048_REWARD_MAXCELL) {
+                const uint32_t cur = max_cell(r0, r1, r2, r3), old = max_cell(bd.x, bd.y, bd.z, bd.w);
+                reward = (float)f.count + ((cur > old) ? (float)(1u << cur) : 0.0f);
+            } else {
+                reward = (float)f.gain;
+            }
+            const float score = a.score[g] + (float)f.gain;
+            const int32_t nstep = a.step[g] + 1;
+
+            // spawn one tile (_spawn2 with count = 1, game_numba.py:733)
+            const uint32_t z0 = occupied_flags(r0) ^ kHi, z1 = occupied_flags(r1) ^ kHi;
+            const uint32_t z2 = occupied_flags(r2) ^ kHi, z3 = occupied_flags(r3) ^ kHi;
+            uint32_t cell, value;
+            if (kRng == ML2048_RNG_REPLAY) {
+                const uint32_t row = (uint32_t)((uint64_t)(a.rand_seed + (int64_t)slot) % (uint64_t)kRandRows);
+                const uint4 perm = __ldg(reinterpret_cast<const uint4 *>(a.randperm) + row);
+                cell = first_empty_in_order(perm, z0, z1, z2, z3);
+                value = 2u - ((a.two_mask >> (cell & 15u)) & 1u);
+            } else {
+                const uint32_t empties = empties16(z0, z1, z2, z3);
+                const uint32_t ne = __popc(empties);
+                cell = ne ? kth_set_bit16(empties, __umulhi(rnd.x, ne)) : 16u;
+                value = (rnd.y < a.two_threshold) ? 1u : 2u;
+            }
+            if (cell < 16u) put_cell(r0, r1, r2, r3, cell, value);
+
+            const uint32_t vm = valid_mask(r0, r1, r2, r3);
+            const bool dead = vm == 0u;
+            reinterpret_cast<uint32_t *>(a.valid_out)[g] = vm;
+            a.reward[g] = reward;
+            a.score[g] = score;
+            a.step[g] = nstep;
+            a.terminated[g] = dead ? 1 : 0;
+            a.invalid[g] = 0;
+            if (kLog) {
+                // expand the sixteen 4-bit counters to the reference's u8[16] `merged`
+                const uint32_t lo = (uint32_t)f.log, hi = (uint32_t)(f.log >> 32);
+                uint32_t m0 = lo & 0xffffu, m1 = lo >> 16, m2 = hi & 0xffffu, m3 = hi >> 16;
+                m0 = (m0 | (m0 << 8)) & 0x00ff00ffu; m0 = (m0 | (m0 << 4)) & 0x0f0f0f0fu;
+                m1 = (m1 | (m1 << 8)) & 0x00ff00ffu; m1 = (m1 | (m1 << 4)) & 0x0f0f0f0fu;
+                m2 = (m2 | (m2 << 8)) & 0x00ff00ffu; m2 = (m2 | (m2 << 4)) & 0x0f0f0f0fu;
+                m3 = (m3 | (m3 << 8)) & 0x00ff00ffu; m3 = (m3 | (m3 << 4)) & 0x0f0f0f0fu;
+                reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(m0, m1, m2, m3);
+            }
+            if (dead && a.stats) {
+                // finished-episode statistics (RunnerStats, runner.py:158-166): rare (~1% of moves)
+                ml2048_stats *st = a.stats + (blockIdx.x % ML2048_STATS_REPLICAS);
+                const unsigned long long sc = (unsigned long long)score;
+                atomicAdd(&st->max_tile_hist[min(max_cell(r0, r1, r2, r3), 19u)], 1ull);
+                atomicAdd(&st->episodes, 1ull);
+                atomicAdd(&st->score_sum, sc);
+                atomicAdd(&st->step_sum, (unsigned long long)nstep);
+                atomicMax(&st->score_max, sc);
+            }
+        } else {
+            // invalid move: only `invalid` changes (game_numba.py:737-738); the board is carried over
+            r0 = bd.x, r1 = bd.y, r2 = bd.z, r3 = bd.w;
+            reinterpret_cast<uint32_t *>(a.valid_out)[g] = valid_mask(r0, r1, r2, r3);
+            a.invalid[g] = 1;
+        }
+        out_board = make_uint4(r0, r1, r2, r3);
+        reinterpret_cast<uint4 *>(a.board_out)[g] = out_board;
+    }
+
+    if (kOneHot != ML2048_ONEHOT_NONE) {
+        sboards[threadIdx.x] = out_board;
+        __syncthreads();
+        const int64_t remaining = a.num_games - block_first;
+        const int games = remaining < kStepThreads ? (int)remaining : kStepThreads;
+        write_onehot_tile<kOneHot == ML2048_ONEHOT_NONE ? ML2048_ONEHOT_F32 : kOneHot, kStepThreads>(sboards, games, a.onehot_out,
+                                                                                                      block_first);
+    }
+}
+
+// ---- auto-reset (VecGame.prepare, game_numba.py:619-658) -----------------------------------
+// Pass 1: terminated games per tile of 4096 slots.  Pass 2: exclusive scan over tiles (one block),
+// advances the id counter.  Pass 3: per tile, slot-ordered offsets -> ids, reset indices, fresh boards.
+
+__device__ __forceinline__ uint32_t flags16(uint4 t)  // sixteen 0/1 bytes -> 16-bit mask
+{
+    const uint32_t m = 0x10204080u;  // gathers bits 0,8,16,24 into the top nibble
+    return ((t.x * m) >> 28) | (((t.y * m) >> 24) & 0xf0u) | (((t.z * m) >> 20) & 0xf00u) | (((t.w * m) >> 16) & 0xf000u);
+}
+
+__device__ __forceinline__ int block_sum_256(int v, int *smem8)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) smem8[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < kPrepThreads / 32; ++i) t += smem8[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(kPrepThreads) prepare_count_kernel(const uint4 *term16, int64_t n16, int32_t *tile_counts)
+{
+    __shared__ int warp_sums[kPrepThreads / 32];
+    const int64_t i = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x;
+    int c = 0;
+    if (i < n16) c = __popc(flags16(term16[i]));
+    const int total = block_sum_256(c, warp_sums);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+// scratch layout: [0, tiles) tile counts -> exclusive offsets; then (8-byte aligned) int64 id_base
+__global__ void __launch_bounds__(1024) prepare_scan_kernel(int32_t *tile_counts, int tiles, int64_t *id_base_slot,
+                                                            int64_t *game_count, int advance, int64_t *reset_count)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = (i < tiles) ? tile_counts[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o) inc += n;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += warp_tot[w];
+        const int carry = carry_s;
+        if (i < tiles) tile_counts[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + wbase + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int64_t total = carry_s;
+        const int64_t base = *game_count;
+        *id_base_slot = base;
+        if (advance) *game_count = base + total;
+        *reset_count = total;
+    }
+}
+
+template <int kRng>
+__global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml2048_prepare_args a, const int32_t *tile_offsets,
+                                                                     const int64_t *id_base_slot)
+{
+    __shared__ int warp_tot[kPrepThreads / 32];
+    const int64_t n16 = (a.num_games + 15) / 16;
+    const int64_t i = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x;
+    uint32_t mask = 0u;
+    if (i < n16) mask = flags16(reinterpret_cast<const uint4 *>(a.terminated)[i]);
+    const int mine = __popc(mask);
+    // exclusive scan of `mine` over the block
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += n;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += warp_tot[w];
+    if (mask == 0u) return;
+
+    int64_t order = (int64_t)tile_offsets[blockIdx.x] + wbase + inc - mine;  // rank among all reset slots
+    const int64_t id_base = *id_base_slot + (a.id_offset ? *a.id_offset : 0);
+    uint4 clear16 = reinterpret_cast<const uint4 *>(a.terminated)[i];
+
+    while (mask) {
+        const int j = __ffs((int)mask) - 1;
+        mask &= mask - 1u;
+        const int64_t g = i * 16 + j;
+        const uint64_t slot = (uint64_t)(a.slot_base + g);
+        uint32_t c0, c1, v0, v1;
+        if (kRng == ML2048_RNG_REPLAY) {
+            // the board is empty, so the first two entries of the table row are taken (game_numba.py:648-655)
+            const uint32_t row = (uint32_t)((uint64_t)(a.rand_base + (int64_t)slot) % (uint64_t)kRandRows);
+            const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(a.randperm) + row * 4);
+            c0 = p & 0xffu;
+            c1 = (p >> 8) & 0xffu;
+            v0 = 2u - ((a.two_mask >> (c0 & 15u)) & 1u);
+            v1 = 2u - ((a.two_mask >> (c1 & 15u)) & 1u);
+        } else {
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)a.philox_counter,
+                                                       (uint32_t)(a.philox_counter >> 32) ^ 0x80000000u),
+                                            make_uint2((uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32)));
+            c0 = rnd.x >> 28;
+            c1 = __umulhi(rnd.y, 15u);
+            c1 += (c1 >= c0) ? 1u : 0u;
+            v0 = (rnd.z < a.two_threshold) ? 1u : 2u;
+            v1 = (rnd.w < a.two_threshold) ? 1u : 2u;
+        }
+        uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u;
+        put_cell(r0, r1, r2, r3, c0 & 15u, v0);
+        put_cell(r0, r1, r2, r3, c1 & 15u, v1);
+        const uint4 bd = make_uint4(r0, r1, r2, r3);
+        reinterpret_cast<uint4 *>(a.board)[g] = bd;
+        reinterpret_cast<uint32_t *>(a.valid)[g] = valid_mask(r0, r1, r2, r3);
+        a.id[g] = (int32_t)(id_base + order);
+        a.step[g] = 0;
+        a.score[g] = 0.0f;
+        a.reward[g] = 0.0f;
+        a.invalid[g] = 0;
+        if (a.merged) reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(0, 0, 0, 0);
+        if (a.reset_indices) a.reset_indices[order] = g;
+        if (a.onehot) write_onehot_single_dyn(a.onehot_dtype, bd, a.onehot, g);
+        order += 1;
+    }
+    // every flag this thread saw is now cleared (entry.fill(0), game_numba.py:638-639)
+    clear16 = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4 *>(a.terminated)[i] = clear16;
+}
+
+// ---- small stand-alone ops ------------------------------------------------------------------
+
+template <int kDtype>
+__global__ void __launch_bounds__(kStepThreads) onehot_kernel(const uint4 *boards, void *out, int64_t num_games)
+{
+    __shared__ uint4 sboards[kStepThreads];
+    const int64_t block_first = (int64_t)blockIdx.x * kStepThreads;
+    const int64_t g = block_first + threadIdx.x;
+    sboards[threadIdx.x] = (g < num_games) ? boards[g] : make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const int64_t remaining = num_games - block_first;
+    write_onehot_tile<kDtype, kStepThreads>(sboards, remaining < kStepThreads ? (int)remaining : kStepThreads, out, block_first);
+}
+
+__global__ void __launch_bounds__(kStepThreads) valid_kernel(const uint4 *boards, uint32_t *valid, int64_t num_games)
+{
+    const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+    if (g >= num_games) return;
+    const uint4 b = boards[g];
+    valid[g] = valid_mask(b.x, b.y, b.z, b.w);
+}
+
+__global__ void __launch_bounds__(kStepThreads) max_tile_hist_kernel(const uint4 *boards, const uint8_t *terminated,
+                                                                     int64_t num_games, unsigned long long *hist20)
+{
+    __shared__ unsigned int sh[20];
+    if (threadIdx.x < 20) sh[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x; g < num_games; g += (int64_t)gridDim.x * kStepThreads) {
+        if (terminated && !terminated[g]) continue;
+        const uint4 b = boards[g];
+        atomicAdd(&sh[min(max_cell(b.x, b.y, b.z, b.w), 19u)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 20 && sh[threadIdx.x]) atomicAdd(&hist20[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(kStepThreads) sample_random_valid_kernel(const uint32_t *valid, uint8_t *actions, int64_t num_games,
+                                                                           int64_t slot_base, uint64_t seed, uint64_t counter)
+{
+    const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+    if (g >= num_games) return;
+    const uint64_t slot = (uint64_t)(slot_base + g);
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t vm = valid[g];
+    const uint32_t bits = (vm & 1u) | ((vm >> 7) & 2u) | ((vm >> 14) & 4u) | ((vm >> 21) & 8u);
+    const uint32_t nv = __popc(bits);
+    actions[g] = (uint8_t)(nv ? kth_set_bit16(bits, __umulhi(rnd.z, nv)) : 0u);
+}
+
+__global__ void fill_terminated_kernel(uint8_t *terminated, int64_t num_games, int64_t padded)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < padded) terminated[i] = (i < num_games) ? 1 : 0;
+}
+
+// ---- launch helpers -------------------------------------------------------------------------
+
+inline bool misaligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
+
+inline int launch_status()
+{
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+template <int kRng, bool kLog>
+int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)((a.num_games + kStepThreads - 1) / kStepThreads);
+    switch (a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE) {
+    case ML2048_ONEHOT_NONE: step_kernel<kRng, kLog, ML2048_ONEHOT_NONE><<<grid, kStepThreads, 0, s>>>(a); break;
+    case ML2048_ONEHOT_F32: step_kernel<kRng, kLog, ML2048_ONEHOT_F32><<<grid, kStepThreads, 0, s>>>(a); break;
+    case ML2048_ONEHOT_BF16: step_kernel<kRng, kLog, ML2048_ONEHOT_BF16><<<grid, kStepThreads, 0, s>>>(a); break;
+    case ML2048_ONEHOT_U8: step_kernel<kRng, kLog, ML2048_ONEHOT_U8><<<grid, kStepThreads, 0, s>>>(a); break;
+    default: return ML2048_E_ENUM;
+    }
+    return launch_status();
+}
+
+}  // namespace
+
+// ---- C ABI ----------------------------------------------------------------------------------
+
+extern "C" {
+
+int ml2048_abi_version(void) { return ML2048_ABI_VERSION; }
+
+int64_t ml2048_prepare_scratch_ints(int64_t num_games)
+{
+    if (num_games <= 0) return 0;
+    const int64_t tiles = (num_games + kPrepTile - 1) / kPrepTile;
+    return ((tiles + 1) / 2) * 2 + 2;  // tile counts (padded to 8 bytes) + one int64
+}
+
+int ml2048_step(const ml2048_step_args *args, void *stream)
+{
+    if (!args) return ML2048_E_NULL;
+    if (args->struct_size != sizeof(ml2048_step_args)) return ML2048_E_STRUCT;
+    const ml2048_step_args &a = *args;
+    if (a.num_games <= 0) return ML2048_E_SIZE;
+    if (!a.board_in || !a.board_out || !a.valid_out || !a.step || !a.score || !a.reward || !a.terminated || !a.invalid)
+        return ML2048_E_NULL;
+    if (a.board_in == a.board_out) return ML2048_E_NULL;
+    if (misaligned(a.board_in, 16) || misaligned(a.board_out, 16) || misaligned(a.valid_out, 4) || misaligned(a.merged, 16) ||
+        misaligned(a.onehot_out, 16) || misaligned(a.valid_in, 4) || misaligned(a.randperm, 16) || misaligned(a.stats, 8))
+        return ML2048_E_ALIGN;
+    if (a.reward_kind < 0 || a.reward_kind > ML2048_REWARD_MAXCELL) return ML2048_E_ENUM;
+    if (a.action_mode == ML2048_ACTIONS_GIVEN) {
+        if (!a.actions) return ML2048_E_NULL;
+        if (a.action_dtype < 0 || a.action_dtype > ML2048_ACT_I64) return ML2048_E_ENUM;
+        if (misaligned(a.actions, a.action_dtype == ML2048_ACT_I64 ? 8 : (a.action_dtype == ML2048_ACT_I32 ? 4 : 1)))
+            return ML2048_E_ALIGN;
+    } else if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
+        if (!a.valid_in) return ML2048_E_NULL;
+    } else {
+        return ML2048_E_ENUM;
+    }
+    if (a.onehot_out && (a.onehot_dtype < ML2048_ONEHOT_F32 || a.onehot_dtype > ML2048_ONEHOT_U8)) return ML2048_E_ENUM;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (a.rng_mode == ML2048_RNG_REPLAY) {
+        if (!a.randperm) return ML2048_E_NULL;
+        return a.merged ? launch_step_onehot<ML2048_RNG_REPLAY, true>(a, s) : launch_step_onehot<ML2048_RNG_REPLAY, false>(a, s);
+    }
+    if (a.rng_mode == ML2048_RNG_PHILOX)
+        return a.merged ? launch_step_onehot<ML2048_RNG_PHILOX, true>(a, s) : launch_step_onehot<ML2048_RNG_PHILOX, false>(a, s);
+    return ML2048_E_ENUM;
+}
+
+static int check_prepare_args(const ml2048_prepare_args *args)
+{
+    if (!args) return ML2048_E_NULL;
+    if (args->struct_size != sizeof(ml2048_prepare_args)) return ML2048_E_STRUCT;
+    const ml2048_prepare_args &a = *args;
+    if (a.num_games <= 0) return ML2048_E_SIZE;
+    if (!a.board || !a.valid || !a.id || !a.step || !a.score || !a.reward || !a.terminated || !a.invalid || !a.game_count ||
+        !a.reset_count || !a.scratch)
+        return ML2048_E_NULL;
+    if (misaligned(a.board, 16) || misaligned(a.valid, 4) || misaligned(a.terminated, 16) || misaligned(a.merged, 16) ||
+        misaligned(a.onehot, 16) || misaligned(a.randperm, 16) || misaligned(a.scratch, 8) || misaligned(a.game_count, 8) ||
+        misaligned(a.reset_count, 8) || misaligned(a.reset_indices, 8) || misaligned(a.id_offset, 8))
+        return ML2048_E_ALIGN;
+    if (a.onehot && (a.onehot_dtype < ML2048_ONEHOT_F32 || a.onehot_dtype > ML2048_ONEHOT_U8)) return ML2048_E_ENUM;
+    if (a.rng_mode == ML2048_RNG_REPLAY && !a.randperm) return ML2048_E_NULL;
+    if (a.rng_mode != ML2048_RNG_REPLAY && a.rng_mode != ML2048_RNG_PHILOX) return ML2048_E_ENUM;
+    return 0;
+}
+
+static inline int64_t *prepare_id_base_slot(const ml2048_prepare_args &a, int tiles)
+{
+    return reinterpret_cast<int64_t *>(a.scratch + ((tiles + 1) / 2) * 2);
+}
+
+int ml2048_prepare_count(const ml2048_prepare_args *args, void *stream)
+{
+    const int rc = check_prepare_args(args);
+    if (rc) return rc;
+    const ml2048_prepare_args &a = *args;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t n16 = (a.num_games + 15) / 16;
+    const int tiles = (int)((a.num_games + kPrepTile - 1) / kPrepTile);
+    prepare_count_kernel<<<tiles, kPrepThreads, 0, s>>>(reinterpret_cast<const uint4 *>(a.terminated), n16, a.scratch);
+    prepare_scan_kernel<<<1, 1024, 0, s>>>(a.scratch, tiles, prepare_id_base_slot(a, tiles), a.game_count, a.id_offset ? 0 : 1,
+                                           a.reset_count);
+    return launch_status();
+}
+
+int ml2048_prepare_apply(const ml2048_prepare_args *args, void *stream)
+{
+    const int rc = check_prepare_args(args);
+    if (rc) return rc;
+    const ml2048_prepare_args &a = *args;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int tiles = (int)((a.num_games + kPrepTile - 1) / kPrepTile);
+    if (a.rng_mode == ML2048_RNG_REPLAY)
+        prepare_apply_kernel<ML2048_RNG_REPLAY><<<tiles, kPrepThreads, 0, s>>>(a, a.scratch, prepare_id_base_slot(a, tiles));
+    else
+        prepare_apply_kernel<ML2048_RNG_PHILOX><<<tiles, kPrepThreads, 0, s>>>(a, a.scratch, prepare_id_base_slot(a, tiles));
+    return launch_status();
+}
+
+int ml2048_prepare(const ml2048_prepare_args *args, void *stream)
+{
+    const int rc = ml2048_prepare_count(args, stream);
+    if (rc) return rc;
+    return ml2048_prepare_apply(args, stream);
+}
+
+int ml2048_reset_state(void *board_a, void *board_b, void *valid_a, void *valid_b, int32_t *id, int32_t *step, float *score,
+                       float *reward, uint8_t *terminated, uint8_t *invalid, uint8_t *merged, int64_t num_games, void *stream)
+{
+    if (num_games <= 0) return ML2048_E_SIZE;
+    if (!board_a || !board_b || !valid_a || !valid_b || !id || !step || !score || !reward || !terminated || !invalid)
+        return ML2048_E_NULL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)num_games;
+    cudaMemsetAsync(board_a, 0, n * 16, s);
+    cudaMemsetAsync(board_b, 0, n * 16, s);
+    cudaMemsetAsync(valid_a, 0, n * 4, s);
+    cudaMemsetAsync(valid_b, 0, n * 4, s);
+    cudaMemsetAsync(id, 0, n * 4, s);
+    cudaMemsetAsync(step, 0, n * 4, s);
+    cudaMemsetAsync(score, 0, n * 4, s);
+    cudaMemsetAsync(reward, 0, n * 4, s);
+    cudaMemsetAsync(invalid, 0, n, s);
+    if (merged) cudaMemsetAsync(merged, 0, n * 16, s);
+    const int64_t padded = (num_games + 15) / 16 * 16;
+    fill_terminated_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, s>>>(terminated, num_games, padded);
+    return launch_status();
+}
+
+int ml2048_encode_onehot(const void *board, void *out, int32_t onehot_dtype, int64_t num_games, void *stream)
+{
+    if (num_games <= 0) return ML2048_E_SIZE;
+    if (!board || !out) return ML2048_E_NULL;
+    if (misaligned(board, 16) || misaligned(out, 16)) return ML2048_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((num_games + kStepThreads - 1) / kStepThreads);
+    const uint4 *b = reinterpret_cast<const uint4 *>(board);
+    switch (onehot_dtype) {
+    case ML2048_ONEHOT_F32: onehot_kernel<ML2048_ONEHOT_F32><<<grid, kStepThreads, 0, s>>>(b, out, num_games); break;
+    case ML2048_ONEHOT_BF16: onehot_kernel<ML2048_ONEHOT_BF16><<<grid, kStepThreads, 0, s>>>(b, out, num_games); break;
+    case ML2048_ONEHOT_U8: onehot_kernel<ML2048_ONEHOT_U8><<<grid, kStepThreads, 0, s>>>(b, out, num_games); break;
+    default: return ML2048_E_ENUM;
+    }
+    return launch_status();
+}
+
+int ml2048_valid_actions(const void *board, void *valid_out, int64_t num_games, void *stream)
+{
+    if (num_games <= 0) return ML2048_E_SIZE;
+    if (!board || !valid_out) return ML2048_E_NULL;
+    if (misaligned(board, 16) || misaligned(valid_out, 4)) return ML2048_E_ALIGN;
+    const unsigned grid = (unsigned)((num_games + kStepThreads - 1) / kStepThreads);
+    valid_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4 *>(board),
+                                                                                reinterpret_cast<uint32_t *>(valid_out), num_games);
+    return launch_status();
+}
+
+int ml2048_max_tile_hist(const void *board, const uint8_t *terminated, int64_t num_games, unsigned long long *hist20, void *stream)
+{
+    if (num_games <= 0) return ML2048_E_SIZE;
+    if (!board || !hist20) return ML2048_E_NULL;
+    if (misaligned(board, 16) || misaligned(hist20, 8)) return ML2048_E_ALIGN;
+    int64_t grid = (num_games + kStepThreads - 1) / kStepThreads;
+    if (grid > 148 * 8) grid = 148 * 8;
+    max_tile_hist_kernel<<<(unsigned)grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint4 *>(board), terminated, num_games, hist20);
+    return launch_status();
+}
+
+int ml2048_sample_random_valid(const void *valid, uint8_t *actions_out, int64_t num_games, int64_t slot_base, uint64_t philox_seed,
+                               uint64_t philox_counter, void *stream)
+{
+    if (num_games <= 0) return ML2048_E_SIZE;
+    if (!valid || !actions_out) return ML2048_E_NULL;
+    if (misaligned(valid, 4)) return ML2048_E_ALIGN;
+    const unsigned grid = (unsigned)((num_games + kStepThreads - 1) / kStepThreads);
+    sample_random_valid_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint32_t *>(valid), actions_out, num_games, slot_base, philox_seed, philox_counter);
+    return launch_status();
+}
+
+uint32_t ml2048_two_mask(const float *host_randfloat16, double two_prob)
+{
+    // game_numba.py:207: `randfloat[idx] < two_prob` with idx the CELL index, f32 promoted to f64
+    uint32_t m = 0;
+    if (!host_randfloat16) return 0;
+    for (int c = 0; c < 16; ++c)
+        if ((double)host_randfloat16[c] < two_prob) m |= 1u << c;
+    return m;
+}
+
+uint32_t ml2048_two_threshold(double two_prob)
+{
+    if (!(two_prob > 0.0)) return 0u;
+    if (two_prob >= 1.0) return 0xffffffffu;
+    return (uint32_t)(two_prob * 4294967296.0);
+}
+
+}  // extern "C"

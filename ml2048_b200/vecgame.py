@@ -1,0 +1,546 @@
+"""
+``VecGame`` -- the B200-native drop-in for the reference's vectorised 2048 environment.
+
+Same class surface as the reference (reference: src/ml2048/game_numba.py:522-698):
+
+    VecGame(size, reward_fn=None, *, two_prob=0.8, reuse_state=False)
+    .reset(seed)  .prepare() -> (indices,)  .observations() -> (board, valid)
+    .step(actions) -> VecStepResult  .summary()   attributes: ._size ._data ._game_count
+
+but all per-game state lives in HBM as struct-of-arrays torch CUDA tensors and every per-step
+computation is a hand-written sm_100a kernel behind the C ABI of ``include/ml2048_b200.h``.
+Host code here only (a) draws the reference's state-independent host random numbers
+(``host_rng.py``), (b) passes pointers, (c) copies results to the host when the caller asked for
+NumPy.  There is no CPU implementation of the game in this package.
+
+Keyword-only extras (not in the reference):
+    device        CUDA device (default: current)
+    output        "numpy" (default, drop-in for the unmodified VecRunner: results are host arrays)
+                  or "torch" (results are views of the live CUDA tensors; no host copies)
+    rng_mode      "replay" (default; bit-exact with the reference) or "philox" (counter-based, no tables)
+    onehot        None | "f32" | "bf16" | "u8": fuse the CNN's one-hot board encoding
+                  (policy/_network.py:86-95) into step()/prepare(); read it with observations_onehot()
+    track_merged  keep the per-game ``merged`` array (default True, as the reference)
+    slot_base     global slot of game 0 (multi-GPU sharding: results do not depend on the shard count)
+    sync_free     prepare() returns (None,) and never synchronises (CUDA-graph / benchmark loops)
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .host_rng import RAND_ROWS, NumpySchedule
+from .rewards import reward_kind
+
+_ONEHOT = {
+    None: (_lib.ONEHOT_NONE, None),
+    "f32": (_lib.ONEHOT_F32, torch.float32),
+    "bf16": (_lib.ONEHOT_BF16, torch.bfloat16),
+    "u8": (_lib.ONEHOT_U8, torch.uint8),
+}
+
+# the reference's record layout (game_numba.py:537-551), used by the `_data` compatibility view
+DATA_DTYPE = np.dtype(
+    [
+        ("id", np.int32, ()),
+        ("step", np.int32, ()),
+        ("score", np.float32, ()),
+        ("reward", np.float32, ()),
+        ("board", np.uint8, (16,)),
+        ("merged", np.uint8, (16,)),
+        ("valid_actions", np.uint8, (4,)),
+        ("terminated", np.uint8, ()),
+        ("invalid", np.uint8, ()),
+        ("_padding", np.uint8, 10),
+    ],
+    align=True,
+)
+
+
+class VecStepResult(dict):
+    """The 10-key result of ``step()`` (game_numba.py:507-519, 687-698).
+
+    In the reference the values are views of live arrays.  Here they are fetched from the live device
+    tensors when a key is first read (NumPy mode: one D2H copy of exactly that field; torch mode: a
+    view of the CUDA tensor), which gives the same "current contents" semantics without copying
+    fields nobody reads."""
+
+    KEYS = ("state", "valid_actions", "merged", "step", "reward", "score", "terminated", "invalid", "prev_state",
+            "prev_valid_actions")
+
+    def __init__(self, env: "VecGame"):
+        super().__init__()
+        self._env = env
+
+    def __missing__(self, key: str):
+        if key not in self.KEYS:
+            raise KeyError(key)
+        value = self._env._fetch(key)
+        self[key] = value
+        return value
+
+    def __contains__(self, key: object) -> bool:
+        return key in self.KEYS
+
+    def keys(self):
+        return list(self.KEYS)
+
+    def items(self):
+        return [(k, self[k]) for k in self.KEYS]
+
+    def values(self):
+        return [self[k] for k in self.KEYS]
+
+    def __iter__(self):
+        return iter(self.KEYS)
+
+    def __len__(self) -> int:
+        return len(self.KEYS)
+
+
+class _DataView:
+    """Stand-in for the reference's structured array ``VecGame._data`` (game_numba.py:571).
+
+    ``view["id"]`` copies one field to the host; ``view[slot]`` / ``view[indices]`` gathers whole
+    64-byte records (replay.py:147-151 reads ``game._data[slot]["id"].item()``)."""
+
+    def __init__(self, env: "VecGame"):
+        self._env = env
+
+    def __len__(self) -> int:
+        return self._env._size
+
+    @property
+    def dtype(self) -> np.dtype:
+        return DATA_DTYPE
+
+    def __getitem__(self, key: Any):
+        env = self._env
+        if isinstance(key, str):
+            name = {"board": "state"}.get(key, key)
+            if key == "id":
+                return env._to_host(env._id)
+            if key == "_padding":
+                return np.zeros((env._size, 10), np.uint8)
+            return env._fetch(name, force_host=True)
+        scalar = isinstance(key, (int, np.integer))
+        idx = torch.as_tensor(np.atleast_1d(np.arange(env._size)[key]), device=env.device, dtype=torch.long)
+        rec = np.zeros((idx.numel(),), dtype=DATA_DTYPE)
+        cur = env._cur
+        rec["id"] = env._id[idx].cpu().numpy()
+        rec["step"] = env._step[idx].cpu().numpy()
+        rec["score"] = env._score[idx].cpu().numpy()
+        rec["reward"] = env._reward[idx].cpu().numpy()
+        rec["board"] = env._board[cur][idx].cpu().numpy()
+        if env._merged is not None:
+            rec["merged"] = env._merged[idx].cpu().numpy()
+        rec["valid_actions"] = env._valid[cur][idx].cpu().numpy()
+        rec["terminated"] = env._terminated[idx].cpu().numpy()
+        rec["invalid"] = env._invalid[idx].cpu().numpy()
+        return rec[0] if scalar else rec
+
+    def copy(self) -> np.ndarray:
+        return self[:]
+
+
+class VecGame:
+    """Vectorised 2048 on one B200.  See the module docstring."""
+
+    _RAND_SIZE: int = RAND_ROWS
+    _DATA_DTYPE = DATA_DTYPE
+
+    def __init__(
+        self,
+        size: int,
+        reward_fn: Any = None,
+        *,
+        two_prob: float = 0.8,
+        reuse_state: bool = False,
+        device: Any = None,
+        output: str = "numpy",
+        rng_mode: str = "replay",
+        onehot: Optional[str] = None,
+        track_merged: bool = True,
+        slot_base: int = 0,
+        sync_free: bool = False,
+    ):
+        if size <= 0:
+            raise ValueError(f"size={size}")  # game_numba.py:561-562
+        if output not in ("numpy", "torch"):
+            raise ValueError(f"output={output!r}")
+        if rng_mode not in ("replay", "philox"):
+            raise ValueError(f"rng_mode={rng_mode!r}")
+        if onehot not in _ONEHOT:
+            raise ValueError(f"onehot={onehot!r}")
+        self._lib = _lib.load()  # raises if the CUDA library is missing: no fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError("ml2048_b200.VecGame needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError(f"device={device!r}: ml2048_b200 runs on CUDA only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+
+        self._size = int(size)
+        self._two_prob = float(two_prob)
+        self._reuse_state = reuse_state  # stored and unused, like the reference (game_numba.py:569)
+        self._reward_fn = reward_fn
+        self._reward_kind = reward_kind(reward_fn)
+        self._output = output
+        self._rng_mode = _lib.RNG_REPLAY if rng_mode == "replay" else _lib.RNG_PHILOX
+        self._onehot_kind, onehot_dtype = _ONEHOT[onehot]
+        self._slot_base = int(slot_base)
+        self._sync_free = bool(sync_free)
+
+        m, dev = self._size, self.device
+        pad = (m + 15) // 16 * 16
+        with torch.cuda.device(dev):
+            self._board = torch.zeros((2, m, 16), dtype=torch.uint8, device=dev)
+            self._valid = torch.zeros((2, m, 4), dtype=torch.uint8, device=dev)
+            self._id = torch.zeros((m,), dtype=torch.int32, device=dev)
+            self._step = torch.zeros((m,), dtype=torch.int32, device=dev)
+            self._score = torch.zeros((m,), dtype=torch.float32, device=dev)
+            self._reward = torch.zeros((m,), dtype=torch.float32, device=dev)
+            self._terminated_padded = torch.zeros((pad,), dtype=torch.uint8, device=dev)
+            self._terminated = self._terminated_padded[:m]
+            self._invalid = torch.zeros((m,), dtype=torch.uint8, device=dev)
+            self._merged = torch.zeros((m, 16), dtype=torch.uint8, device=dev) if track_merged else None
+            self._onehot = torch.zeros((m, 16, 16), dtype=onehot_dtype, device=dev) if onehot_dtype is not None else None
+            self._actions_dev = torch.zeros((m,), dtype=torch.int64, device=dev)  # staging for host actions
+            self._actions_out = torch.zeros((m,), dtype=torch.uint8, device=dev)
+            self._randperm_dev = torch.zeros((RAND_ROWS, 16), dtype=torch.uint8, device=dev)
+            self._game_count_dev = torch.zeros((1,), dtype=torch.int64, device=dev)  # survives reset(), :582
+            self._reset_count_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
+            self._reset_indices_dev = torch.zeros((m,), dtype=torch.int64, device=dev)
+            self._id_offset_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
+            n_scratch = int(self._lib.ml2048_prepare_scratch_ints(m))
+            self._scratch = torch.zeros((n_scratch,), dtype=torch.int32, device=dev)
+            self._stats_dev = torch.zeros((_lib.STATS_REPLICAS, _lib.STATS_WORDS), dtype=torch.int64, device=dev)
+        self._cur = 0
+        self._host: dict[str, torch.Tensor] = {}  # pinned staging buffers, one per fetched field
+
+        # host copies of the random tables, as in the reference (game_numba.py:577-580)
+        self._randperm = np.empty((RAND_ROWS, 16), dtype=np.uint8)
+        self._randfloat = np.empty((RAND_ROWS,), dtype=np.float32)
+        self._rand_step = 0
+        self._two_mask = 0
+        self._two_threshold = int(self._lib.ml2048_two_threshold(self._two_prob))
+        self._philox_seed = 0
+        self._philox_counter = 0
+        self._schedule: Any = None
+        self._dist_group = None
+        self._dist_rank = 0
+        self._dist_world = 1
+
+        self._step_args = _lib.StepArgs()
+        self._prep_args = _lib.PrepareArgs()
+        self._init_args()
+        self.reset()
+
+    # ------------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------------
+
+    @staticmethod
+    def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+        return None if t is None else t.data_ptr()
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _init_args(self) -> None:
+        a = self._step_args
+        a.struct_size = C.sizeof(_lib.StepArgs)
+        a.reward_kind = self._reward_kind
+        a.rng_mode = self._rng_mode
+        a.onehot_dtype = self._onehot_kind
+        a.num_games = self._size
+        a.slot_base = self._slot_base
+        a.step = self._p(self._step)
+        a.score = self._p(self._score)
+        a.reward = self._p(self._reward)
+        a.terminated = self._p(self._terminated_padded)
+        a.invalid = self._p(self._invalid)
+        a.merged = self._p(self._merged)
+        a.onehot_out = self._p(self._onehot)
+        a.randperm = self._p(self._randperm_dev)
+        a.two_threshold = self._two_threshold
+        a.stats = self._p(self._stats_dev)
+        p = self._prep_args
+        p.struct_size = C.sizeof(_lib.PrepareArgs)
+        p.rng_mode = self._rng_mode
+        p.onehot_dtype = self._onehot_kind
+        p.num_games = self._size
+        p.slot_base = self._slot_base
+        p.id = self._p(self._id)
+        p.step = self._p(self._step)
+        p.score = self._p(self._score)
+        p.reward = self._p(self._reward)
+        p.terminated = self._p(self._terminated_padded)
+        p.invalid = self._p(self._invalid)
+        p.merged = self._p(self._merged)
+        p.onehot = self._p(self._onehot)
+        p.randperm = self._p(self._randperm_dev)
+        p.two_threshold = self._two_threshold
+        p.game_count = self._p(self._game_count_dev)
+        p.id_offset = None
+        p.reset_count = self._p(self._reset_count_dev)
+        p.reset_indices = self._p(self._reset_indices_dev)
+        p.scratch = self._p(self._scratch)
+
+    def _to_host(self, t: torch.Tensor, key: Optional[str] = None) -> np.ndarray:
+        """D2H through a pinned staging buffer owned by this environment (reused per field)."""
+        name = key or f"_anon{t.data_ptr()}"
+        buf = self._host.get(name)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._host[name] = buf
+        buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return buf.numpy()
+
+    def _device_field(self, key: str) -> torch.Tensor:
+        cur = self._cur
+        if key == "state":
+            return self._board[cur]
+        if key == "valid_actions":
+            return self._valid[cur]
+        if key == "prev_state":
+            return self._board[1 - cur]
+        if key == "prev_valid_actions":
+            return self._valid[1 - cur]
+        if key == "merged":
+            if self._merged is None:
+                raise KeyError("merged is not tracked (track_merged=False)")
+            return self._merged
+        return {"step": self._step, "reward": self._reward, "score": self._score, "terminated": self._terminated,
+                "invalid": self._invalid}[key]
+
+    def _fetch(self, key: str, force_host: bool = False):
+        t = self._device_field(key)
+        if self._output == "torch" and not force_host:
+            return t
+        return self._to_host(t, key)
+
+    def _upload_tables(self) -> None:
+        """Tables changed on the host: ship the permutations (16 KiB) and fold the 2-vs-4 uniforms into
+        a 16-bit mask (only randfloat[0:16] is ever read, indexed by CELL: game_numba.py:207)."""
+        self._randperm_dev.copy_(torch.from_numpy(self._randperm))
+        self._two_mask = int(self._lib.ml2048_two_mask(self._randfloat.ctypes.data, self._two_prob))
+
+    # ------------------------------------------------------------------------------------------
+    # reference surface
+    # ------------------------------------------------------------------------------------------
+
+    def reset(self, seed: Optional[int] = None, *, schedule: Any = None) -> None:
+        """game_numba.py:606-617.  ``schedule`` (optional) replaces the numpy generator by recorded draws."""
+        self._schedule = schedule if schedule is not None else NumpySchedule(seed)
+        self._rand_step = 0
+        self._randperm[:, :] = np.arange(16).reshape((1, 16))
+        self._schedule.refresh_tables(self._randperm, self._randfloat)
+        self._upload_tables()
+        self._philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF if seed is not None else int(np.random.SeedSequence().entropy) & 0xFFFFFFFFFFFFFFFF
+        self._philox_counter = 0
+        with torch.cuda.device(self.device):
+            rc = self._lib.ml2048_reset_state(
+                self._p(self._board[0]), self._p(self._board[1]), self._p(self._valid[0]), self._p(self._valid[1]),
+                self._p(self._id), self._p(self._step), self._p(self._score), self._p(self._reward),
+                self._p(self._terminated_padded), self._p(self._invalid), self._p(self._merged), self._size, self._stream())
+        _lib.check(rc, "ml2048_reset_state")
+        if self._onehot is not None:
+            self._onehot.zero_()
+            self._onehot[:, 0, :] = 1  # an all-empty board encodes as class 0 everywhere
+        self._stats_dev.zero_()
+        self._cur = 0
+
+    def observations(self):
+        """game_numba.py:586-587: (board (M,16) u8, valid_actions (M,4) u8)."""
+        return self._fetch("state"), self._fetch("valid_actions")
+
+    def observations_onehot(self) -> torch.Tensor:
+        """The fused CNN input, (M,16,16) class-major on the device (policy/_network.py:86-95)."""
+        if self._onehot is None:
+            raise RuntimeError("construct VecGame(..., onehot='f32'|'bf16'|'u8') to fuse the one-hot encoding")
+        return self._onehot
+
+    def prepare(self):
+        """game_numba.py:619-658: refresh tables with probability 0.1, draw an offset, reset every
+        terminated slot in ascending order.  Returns ``(indices,)``."""
+        if self._schedule.refresh_coin() >= 0.9 or self._rand_step >= self._RAND_SIZE:
+            self._rand_step = 0
+            self._schedule.refresh_tables(self._randperm, self._randfloat)
+            self._upload_tables()
+        rand_offset = self._schedule.offset()
+
+        p = self._prep_args
+        cur = self._cur
+        p.board = self._p(self._board[cur])
+        p.valid = self._p(self._valid[cur])
+        p.rand_base = self._rand_step + rand_offset
+        p.two_mask = self._two_mask
+        p.philox_seed = self._philox_seed
+        p.philox_counter = self._philox_counter
+        self._philox_counter += 1
+        stream = self._stream()
+        with torch.cuda.device(self.device):
+            if self._dist_group is None:
+                _lib.check(self._lib.ml2048_prepare(C.byref(p), stream), "ml2048_prepare")
+            else:
+                self._prepare_sharded(p, stream)
+        if self._sync_free:
+            return (None,)
+        n = int(self._reset_count_dev.item())
+        idx = self._reset_indices_dev[:n]
+        if self._output == "torch":
+            return (idx,)
+        if n == 0:
+            return (np.zeros((0,), dtype=np.int64),)
+        return (idx.cpu().numpy(),)
+
+    def step(self, actions) -> VecStepResult:
+        """game_numba.py:660-698.  ``actions``: (M,) integers in 0..3 (NumPy array, CPU or CUDA tensor)."""
+        assert tuple(actions.shape) == (self._size,), actions.shape  # game_numba.py:668
+        rand_offset = self._schedule.offset()  # :670
+
+        a = self._step_args
+        dev_actions, a.action_dtype = self._stage_actions(actions)
+        a.action_mode = _lib.ACTIONS_GIVEN
+        a.actions = dev_actions.data_ptr()
+        a.actions_out = None
+        self._launch_step(self._rand_step + rand_offset)
+        self._rand_step += 1  # :685
+        self._keepalive = dev_actions
+        return VecStepResult(self)
+
+    def summary(self) -> list[Any]:
+        """game_numba.py:593-604: (tile value, count, share) of the max tile over all live boards."""
+        hist = torch.zeros((20,), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.ml2048_max_tile_hist(self._p(self._board[self._cur]), None, self._size, self._p(hist), self._stream())
+        _lib.check(rc, "ml2048_max_tile_hist")
+        counts = hist.cpu().numpy()
+        total = counts.sum()
+        entries = [(2 ** int(k), counts[k], counts[k] / total) for k in range(20) if counts[k]]
+        entries.sort(key=lambda s: s[0], reverse=True)
+        return entries
+
+    @property
+    def _data(self) -> _DataView:
+        return _DataView(self)
+
+    @property
+    def _game_count(self) -> int:
+        return int(self._game_count_dev.item())
+
+    @_game_count.setter
+    def _game_count(self, value: int) -> None:
+        self._game_count_dev.fill_(int(value))
+
+    @property
+    def _prev_state(self):
+        return self._fetch("prev_state")
+
+    @property
+    def _prev_valid_actions(self):
+        return self._fetch("prev_valid_actions")
+
+    # ------------------------------------------------------------------------------------------
+    # extras: device-side policy for synthetic rollouts, statistics, sharding
+    # ------------------------------------------------------------------------------------------
+
+    def step_random(self, *, return_actions: bool = False):
+        """One step with uniformly random VALID actions chosen inside the kernel (Philox) --
+        the benchmark policy (semantics of policy/random.py:17-27), no action array crosses the bus."""
+        rand_offset = self._schedule.offset()
+        a = self._step_args
+        a.action_mode = _lib.ACTIONS_RANDOM_VALID
+        a.action_dtype = _lib.ACT_U8
+        a.actions = None
+        a.actions_out = self._p(self._actions_out) if return_actions else None
+        self._launch_step(self._rand_step + rand_offset)
+        self._rand_step += 1
+        return VecStepResult(self)
+
+    def _launch_step(self, rand_seed: int) -> None:
+        a = self._step_args
+        cur = self._cur
+        a.board_in = self._p(self._board[cur])
+        a.board_out = self._p(self._board[1 - cur])
+        a.valid_in = self._p(self._valid[cur])
+        a.valid_out = self._p(self._valid[1 - cur])
+        a.rand_seed = rand_seed
+        a.two_mask = self._two_mask
+        a.philox_seed = self._philox_seed
+        a.philox_counter = self._philox_counter
+        self._philox_counter += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.ml2048_step(C.byref(a), self._stream()), "ml2048_step")
+        self._cur = 1 - cur
+
+    def _stage_actions(self, actions) -> tuple[torch.Tensor, int]:
+        if isinstance(actions, np.ndarray):
+            if actions.dtype not in (np.int64, np.int32, np.uint8, np.int8):
+                actions = actions.astype(np.int64)
+            actions = torch.from_numpy(np.ascontiguousarray(actions))
+        if not isinstance(actions, torch.Tensor):
+            raise TypeError(f"actions must be a numpy array or torch tensor, got {type(actions)}")
+        if actions.dtype not in (torch.int64, torch.int32, torch.uint8, torch.int8):
+            actions = actions.to(torch.int64)
+        if actions.device != self.device:
+            actions = actions.to(self.device, non_blocking=True)
+        actions = actions.contiguous()
+        code = {torch.int64: _lib.ACT_I64, torch.int32: _lib.ACT_I32, torch.uint8: _lib.ACT_U8, torch.int8: _lib.ACT_U8}
+        return actions, code[actions.dtype]
+
+    def episode_stats(self, *, reset: bool = False) -> dict[str, Any]:
+        """Finished-episode statistics accumulated by step(): RunnerStats' max-tile histogram
+        (runner.py:150-166) plus episode count, score and step sums, max score."""
+        raw = self.episode_stats_tensor()
+        if reset:
+            self._stats_dev.zero_()
+        return stats_to_dict(raw.cpu())
+
+    def episode_stats_tensor(self) -> torch.Tensor:
+        """int64[24] on the device: hist[20], episodes, score_sum, step_sum, score_max (replicas folded)."""
+        s = self._stats_dev
+        return torch.cat([s[:, :23].sum(dim=0), s[:, 23:].max(dim=0).values])
+
+    def shard(self, group: Any = None) -> None:
+        """Make game ids globally slot-ordered across the ranks of ``group`` (each rank owning the
+        contiguous global slots [slot_base, slot_base+size)), as in a single-process reference run:
+        prepare() then exchanges per-rank reset counts (one tiny all_gather, no host sync)."""
+        import torch.distributed as dist
+
+        self._dist_group = group if group is not None else dist.group.WORLD
+        self._dist_rank = dist.get_rank(self._dist_group)
+        self._dist_world = dist.get_world_size(self._dist_group)
+        self._counts_all = torch.zeros((self._dist_world,), dtype=torch.int64, device=self.device)
+
+    def _prepare_sharded(self, p: Any, stream: int) -> None:
+        import torch.distributed as dist
+
+        p.id_offset = self._p(self._id_offset_dev)
+        _lib.check(self._lib.ml2048_prepare_count(C.byref(p), stream), "ml2048_prepare_count")
+        dist.all_gather_into_tensor(self._counts_all, self._reset_count_dev, group=self._dist_group)
+        self._id_offset_dev.copy_(self._counts_all[: self._dist_rank].sum().reshape(1))
+        _lib.check(self._lib.ml2048_prepare_apply(C.byref(p), stream), "ml2048_prepare_apply")
+        self._game_count_dev += self._counts_all.sum()
+
+
+def stats_to_dict(raw: torch.Tensor) -> dict[str, Any]:
+    raw = raw.to(torch.int64).cpu().numpy()
+    episodes = int(raw[20])
+    return {
+        "max_tile_hist": raw[:20].copy(),
+        "episodes": episodes,
+        "score_sum": int(raw[21]),
+        "step_sum": int(raw[22]),
+        "score_max": int(raw[23]),
+        "mean_score": (int(raw[21]) / episodes) if episodes else float("nan"),
+        "mean_steps": (int(raw[22]) / episodes) if episodes else float("nan"),
+    }

@@ -1,0 +1,143 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every
+symbol include/ml2048_b200.h declares; the ctypes mirrors match the C structs; host-side logic."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ml2048_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ml2048_b200 import _lib, build
+
+    build.build()  # nvcc cross-compiles without a GPU; no-op when up to date
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from ml2048_b200 import _lib
+
+    text = open(HEADER).read()
+    declared = set(re.findall(r"ML2048_API\s+[\w\s\*]+?\b(ml2048_\w+)\s*\(", text))
+    assert len(declared) >= 13
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ml2048_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header(lib, tmp_path):
+    from ml2048_b200 import _lib
+
+    src = tmp_path / "sz.c"
+    src.write_text(
+        f'#include "{HEADER}"\n#include <stdio.h>\n#include <stddef.h>\n'
+        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu\\n\", sizeof(ml2048_step_args), sizeof(ml2048_prepare_args),"
+        " sizeof(ml2048_stats), offsetof(ml2048_step_args, randperm), offsetof(ml2048_step_args, stats),"
+        " offsetof(ml2048_prepare_args, scratch));return 0;}\n"
+    )
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got == [
+        ctypes.sizeof(_lib.StepArgs),
+        ctypes.sizeof(_lib.PrepareArgs),
+        _lib.STATS_WORDS * 8,
+        _lib.StepArgs.randperm.offset,
+        _lib.StepArgs.stats.offset,
+        _lib.PrepareArgs.scratch.offset,
+    ]
+
+
+def test_argument_errors_without_gpu(lib):
+    from ml2048_b200 import _lib
+
+    assert lib.ml2048_step(None, None) == -1
+    a = _lib.StepArgs()
+    assert lib.ml2048_step(ctypes.byref(a), None) == -5  # struct_size not set
+    a.struct_size = ctypes.sizeof(_lib.StepArgs)
+    assert lib.ml2048_step(ctypes.byref(a), None) == -3  # num_games == 0
+    a.num_games = 8
+    assert lib.ml2048_step(ctypes.byref(a), None) == -1  # null boards
+    assert lib.ml2048_prepare_scratch_ints(0) == 0
+    assert lib.ml2048_prepare_scratch_ints(4096) == 4
+    assert lib.ml2048_prepare_scratch_ints(4097) == 4
+
+
+def test_two_mask_uses_double_compare(lib):
+    # game_numba.py:207: float32(0.8) = 0.800000011920929 is NOT < 0.8 as a double: that cell spawns a 4
+    rf = np.zeros(16, np.float32)
+    rf[3] = np.float32(0.8)
+    rf[5] = np.nextafter(np.float32(0.8), np.float32(0))
+    rf[7] = 0.9
+    mask = lib.ml2048_two_mask(rf.ctypes.data, 0.8)
+    assert mask == (0xFFFF & ~(1 << 3) & ~(1 << 7))
+    assert lib.ml2048_two_threshold(0.0) == 0
+    assert lib.ml2048_two_threshold(1.0) == 0xFFFFFFFF
+    assert lib.ml2048_two_threshold(0.5) == 0x80000000
+
+
+def test_reward_selection_by_identity():
+    import ml2048_b200
+    from ml2048_b200.rewards import reward_kind
+
+    assert reward_kind(None) == 0
+    assert reward_kind(ml2048_b200.reward_fn_improved) == 1
+    assert reward_kind("rank") == 2
+
+    def reward_fn_maxcell(state, prev, merged):  # the reference's own function object is accepted by name
+        return 0.0
+
+    assert reward_kind(reward_fn_maxcell) == 3
+    with pytest.raises(ValueError):
+        reward_kind(lambda s, p, m: 0.0)
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    import ml2048_b200
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ml2048_b200.VecGame(8)
+
+
+def test_host_schedule_matches_oracle_schedule():
+    """The product's host draws (host_rng.py) and the oracle's are the same numpy calls in the same order."""
+    from ml2048_b200.host_rng import NumpySchedule
+    from oracle.oracle import NumpySchedule as OracleSchedule
+
+    for seed in (0, 1, 123):
+        a, b = NumpySchedule(seed), OracleSchedule(seed)
+        pa = np.tile(np.arange(16, dtype=np.uint8), (1024, 1))
+        pb = pa.copy()
+        fa, fb = np.empty(1024, np.float32), np.empty(1024, np.float32)
+        for _ in range(3):
+            a.refresh_tables(pa, fa)
+            b.refresh_tables(pb, fb)
+            assert np.array_equal(pa, pb) and np.array_equal(fa, fb)
+            assert a.refresh_coin() == b.refresh_coin()
+            assert a.offset() == b.offset()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ml2048_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"(import\s+oracle|from\s+oracle|from\s+\.+oracle|liboracle|oracle/)", text), f"{f} reaches into oracle/"
+    code = "import sys; import ml2048_b200, ml2048_b200.vecgame, ml2048_b200.sharding; assert not any(m.startswith('oracle') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)

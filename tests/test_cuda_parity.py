@@ -1,0 +1,445 @@
+"""
+GPU parity tests: the CUDA environment (through the C ABI) against the committed golden fixtures
+generated from the live reference, and against the CPU oracle on seeded inputs.  Bit-exact.
+Run on the B200 box with `pytest -m gpu`.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_rollouts
+from oracle.rollout import compare_rollouts, record_rollout
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ml():
+    import ml2048_b200
+
+    assert torch.cuda.is_available()
+    return ml2048_b200
+
+
+def _make(ml, m, reward="normal", **kw):
+    return ml.VecGame(m, reward, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures from the live reference
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("fname", golden_rollouts())
+def test_rollout_matches_reference_golden(ml, fname):
+    g = golden(fname)
+    m, n, seed, aseed = [int(x) for x in g["meta"]]
+    two_prob, wild = [float(x) for x in g["meta_f"]]
+    env = _make(ml, m, str(g["reward_kind"]), two_prob=two_prob)
+    env.reset(seed)
+    got = record_rollout(env, n, action_seed=aseed, wild=wild, full=True)
+    compare_rollouts(got, g)
+
+
+def test_recorded_schedule_replay(ml):
+    from ml2048_b200.host_rng import RecordedSchedule
+
+    g = golden("schedule_sched_small.npz")
+    m, n, seed, aseed = [int(x) for x in g["meta"]]
+    two_prob, _ = [float(x) for x in g["meta_f"]]
+    env = _make(ml, m, str(g["reward_kind"]), two_prob=two_prob)
+    env.reset(schedule=RecordedSchedule(g["sched_coins"], g["sched_offsets"], g["sched_perms"], g["sched_floats"]))
+    got = record_rollout(env, n, actions=g["actions"], full=True)
+    compare_rollouts(got, g)
+
+
+def test_torch_output_mode_matches_golden(ml):
+    g = golden("rollout_c1_seed0_normal.npz")
+    m, n, seed, _ = [int(x) for x in g["meta"]]
+    env = _make(ml, m, "normal", output="torch")
+    env.reset(seed)
+    for t in range(n):
+        (idx,) = env.prepare()
+        assert idx.is_cuda and idx.dtype == torch.int64
+        res = env.step(torch.from_numpy(g["actions"][t].astype(np.int64)).cuda())
+        assert res["state"].is_cuda
+        np.testing.assert_array_equal(res["state"].cpu().numpy(), g["state"][t])
+        np.testing.assert_array_equal(res["reward"].cpu().numpy().view(np.uint32), g["reward"][t].view(np.uint32))
+        np.testing.assert_array_equal(res["prev_state"].cpu().numpy(), g["prev_state"][t])
+        np.testing.assert_array_equal(res["terminated"].cpu().numpy(), g["terminated"][t])
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.int32, np.uint8, np.int8])
+def test_action_dtypes(ml, dtype):
+    g = golden("rollout_c1_seed0_normal.npz")
+    m, _, seed, _ = [int(x) for x in g["meta"]]
+    env = _make(ml, m, "normal")
+    env.reset(seed)
+    for t in range(8):
+        env.prepare()
+        res = env.step(g["actions"][t].astype(dtype))
+        np.testing.assert_array_equal(res["state"], g["state"][t])
+        np.testing.assert_array_equal(res["invalid"], g["invalid"][t])
+
+
+# ---------------------------------------------------------------------------------------------
+# live oracle, seeded inputs
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize(
+    "m,n,reward,two_prob",
+    [
+        (1, 50, "normal", 0.8),
+        (15, 40, "improved", 0.8),
+        (16, 40, "rank", 0.8),
+        (17, 40, "maxcell", 0.8),
+        (255, 30, "normal", 0.3),
+        (257, 30, "improved", 1.0),
+        (4095, 20, "rank", 0.0),
+        (4097, 200, "maxcell", 0.8),
+        (70001, 150, "improved", 0.8),
+    ],
+)
+def test_rollout_matches_oracle(ml, oracle, m, n, reward, two_prob):
+    seed = 1000 + m
+    ref = oracle.OracleVecGame(m, reward, two_prob=two_prob)
+    ref.reset(seed)
+    want = record_rollout(ref, n, action_seed=m, wild=0.05, full=True)
+    env = _make(ml, m, reward, two_prob=two_prob)
+    env.reset(seed)
+    got = record_rollout(env, n, actions=want["actions"], full=True)
+    compare_rollouts(got, want)
+
+
+def test_full_size_matches_oracle(ml, oracle):
+    """BASELINE sweep size M = 2^22: a handful of lock-step steps against the C oracle, every field."""
+    m, n = 1 << 22, 6
+    ref = oracle.OracleVecGame(m, "improved")
+    ref.reset(11)
+    env = _make(ml, m, "improved")
+    env.reset(11)
+    rng = np.random.default_rng(5)
+    for t in range(n):
+        (i0,) = ref.prepare()
+        (i1,) = env.prepare()
+        np.testing.assert_array_equal(i1, i0)
+        _, valid = ref.observations()
+        acts = oracle.random_valid_actions(valid, rng.random(m))
+        r0 = ref.step(acts)
+        r1 = env.step(acts)
+        for k in ("state", "valid_actions", "merged", "step", "terminated", "invalid", "prev_state", "prev_valid_actions"):
+            np.testing.assert_array_equal(r1[k], r0[k], err_msg=f"{k} step {t}")
+        for k in ("reward", "score"):
+            np.testing.assert_array_equal(r1[k].view(np.uint32), r0[k].view(np.uint32), err_msg=f"{k} step {t}")
+    np.testing.assert_array_equal(env._data["id"], ref._data["id"])
+    assert env._game_count == ref._game_count
+
+
+def _inject(env, boards_np):
+    """Load arbitrary boards into the CUDA environment (mask recomputed by the library)."""
+    from ml2048_b200 import _lib
+
+    b = torch.from_numpy(boards_np).to(env.device)
+    env._board[env._cur].copy_(b)
+    rc = env._lib.ml2048_valid_actions(env._board[env._cur].data_ptr(), env._valid[env._cur].data_ptr(), env._size,
+                                       torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ml2048_valid_actions")
+    valid = env._valid[env._cur]
+    env._terminated.copy_((valid.sum(dim=1) == 0).to(torch.uint8))
+
+
+def test_arbitrary_boards_all_directions(ml, oracle):
+    """Moves, masks, the four rewards and `merged` on the reference-generated board set (exponents up
+    to 15, dead boards, empty boards), every direction, through the real step kernel."""
+    g = golden("boards.npz")
+    boards = g["boards"]
+    m = boards.shape[0]
+    for reward in ("normal", "improved", "rank", "maxcell"):
+        for action in range(4):
+            env = _make(ml, m, reward)
+            env.reset(77)
+            _inject(env, boards)
+            np.testing.assert_array_equal(env.observations()[1], g["mask"])
+            ref = oracle.OracleVecGame(m, reward)
+            ref.reset(77)
+            ref._data["board"] = boards
+            ref._data["valid_actions"] = g["mask"]
+            ref._data["terminated"] = g["mask"].sum(axis=1) == 0
+            acts = np.full((m,), action, dtype=np.int64)
+            ref._schedule.refresh_coin()  # keep both host generators in step (no prepare() on either side)
+            env._schedule.refresh_coin()
+            r0 = ref.step(acts)
+            r1 = env.step(acts)
+            moved_ok = g["mask"][:, action] != 0
+            np.testing.assert_array_equal(r1["invalid"], (~moved_ok).astype(np.uint8))
+            np.testing.assert_array_equal(r1["merged"][moved_ok], g["merged"][moved_ok, action])
+            j = [str(x) for x in g["reward_names"]].index(reward)
+            np.testing.assert_array_equal(r1["reward"][moved_ok].astype(np.float64), g["rewards"][moved_ok, action, j])
+            for k in ("state", "valid_actions", "merged", "step", "terminated", "invalid", "reward", "score"):
+                np.testing.assert_array_equal(r1[k], r0[k], err_msg=f"{k} action {action} reward {reward}")
+
+
+def test_known_answer_playground(ml):
+    # playground.ipynb:3915-3926 / :3901-3906, through the step kernel (the spawn lands on an empty cell)
+    prev = np.array([10, 10, 8, 10, 10, 9, 8, 10, 9, 10, 9, 9, 10, 10, 9, 9], np.uint8)
+    want = np.array([11, 8, 10, 0, 10, 9, 8, 10, 9, 10, 10, 0, 11, 10, 0, 0], np.uint8)
+    for reward, value in (("normal", 6144.0), ("rank", 42.0), ("maxcell", 2052.0)):
+        env = _make(ml, 1, reward)
+        env.reset(0)
+        _inject(env, prev[None, :])
+        res = env.step(np.zeros(1, np.int64))
+        state = res["state"][0]
+        spawned = np.flatnonzero(state != want)
+        assert spawned.size == 1 and want[spawned[0]] == 0 and state[spawned[0]] in (1, 2)
+        assert float(res["reward"][0]) == value
+        assert res["merged"][0].tolist() == [0] * 9 + [2, 2] + [0] * 5
+
+
+def test_out_of_range_actions_are_invalid_moves(ml):
+    env = _make(ml, 64)
+    env.reset(1)
+    env.prepare()
+    before = env.observations()[0].copy()
+    res = env.step(np.full(64, 7, np.int64))
+    assert res["invalid"].all()
+    np.testing.assert_array_equal(res["state"], before)
+    res = env.step(np.full(64, -1, np.int64))
+    assert res["invalid"].all()
+
+
+def test_ctor_and_shape_errors(ml):
+    with pytest.raises(ValueError):
+        ml.VecGame(0)
+    with pytest.raises(ValueError):
+        ml.VecGame(4, reward_fn=lambda s, p, m: 0.0)
+    env = ml.VecGame(4)
+    with pytest.raises(AssertionError):
+        env.step(np.zeros(5, np.int64))
+
+
+def test_data_view_and_summary(ml, oracle):
+    m = 300
+    ref = oracle.OracleVecGame(m)
+    ref.reset(9)
+    env = _make(ml, m)
+    env.reset(9)
+    rec = record_rollout(ref, 60, action_seed=1, wild=0.0, full=False)
+    record_rollout(env, 60, actions=rec["actions"], full=False)
+    d = env._data
+    for slot in (0, 17, m - 1):
+        assert d[slot]["id"].item() == int(ref._data[slot]["id"])  # replay.py:147-151 usage
+        np.testing.assert_array_equal(d[slot]["board"], ref._data[slot]["board"])
+    np.testing.assert_array_equal(d["score"], ref._data["score"])
+    assert [(a, int(b)) for a, b, _ in env.summary()] == [(a, int(b)) for a, b, _ in ref.summary()]
+
+
+# ---------------------------------------------------------------------------------------------
+# fused one-hot observation
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("kind,dtype", [("f32", torch.float32), ("bf16", torch.bfloat16), ("u8", torch.uint8)])
+@pytest.mark.parametrize("m", [1, 255, 1024, 5000])
+def test_fused_onehot_matches_reference_encoding(ml, oracle, kind, dtype, m):
+    import torch.nn.functional as F
+
+    env = _make(ml, m, onehot=kind, output="torch")
+    env.reset(21)
+    rng = np.random.default_rng(3)
+    for t in range(40):
+        env.prepare()
+        board, valid = env.observations()
+        oh = env.observations_onehot()
+        assert oh.dtype == dtype and oh.shape == (m, 16, 16)
+        # policy/_network.py:86-95
+        want = F.one_hot(board.long(), 16).float().permute(0, 2, 1)
+        assert torch.equal(oh.float(), want), f"after prepare, step {t}"
+        acts = oracle.random_valid_actions(valid.cpu().numpy(), rng.random(m))
+        res = env.step(acts)
+        want = F.one_hot(res["state"].long(), 16).float().permute(0, 2, 1)
+        assert torch.equal(env.observations_onehot().float(), want), f"after step {t}"
+    np.testing.assert_array_equal(env.observations_onehot().float().cpu().numpy(), oracle.onehot(env.observations()[0].cpu().numpy()))
+
+
+def test_standalone_encode_onehot(ml, oracle):
+    from ml2048_b200 import _lib
+
+    boards = golden("boards.npz")["boards"]
+    boards = np.minimum(boards, 17)
+    b = torch.from_numpy(boards).cuda()
+    lib = _lib.load()
+    for code, dtype in ((_lib.ONEHOT_F32, torch.float32), (_lib.ONEHOT_BF16, torch.bfloat16), (_lib.ONEHOT_U8, torch.uint8)):
+        out = torch.empty((boards.shape[0], 16, 16), dtype=dtype, device="cuda")
+        _lib.check(lib.ml2048_encode_onehot(b.data_ptr(), out.data_ptr(), code, boards.shape[0],
+                                            torch.cuda.current_stream().cuda_stream), "encode")
+        np.testing.assert_array_equal(out.float().cpu().numpy(), oracle.onehot(boards))
+
+
+# ---------------------------------------------------------------------------------------------
+# statistics, device policy, Philox mode, sharding invariance
+# ---------------------------------------------------------------------------------------------
+
+
+def test_episode_stats_match_runner_stats(ml, oracle):
+    """Device statistics == RunnerStats (runner.py:120-166) computed on the host from the results."""
+    m, n = 2000, 400
+    env = _make(ml, m)
+    env.reset(5)
+    rng = np.random.default_rng(8)
+    hist = np.zeros(20, np.int64)
+    episodes = score_sum = step_sum = score_max = 0
+    for _ in range(n):
+        env.prepare()
+        valid = env.observations()[1]
+        res = env.step(oracle.random_valid_actions(valid, rng.random(m)))
+        term = res["terminated"].astype(bool)
+        mx = res["state"][term].max(axis=1) if term.any() else np.zeros(0, np.int64)
+        np.add.at(hist, mx, 1)
+        episodes += int(term.sum())
+        score_sum += int(res["score"][term].sum())
+        step_sum += int(res["step"][term].sum())
+        score_max = max(score_max, int(res["score"][term].max()) if term.any() else 0)
+    st = env.episode_stats()
+    np.testing.assert_array_equal(st["max_tile_hist"], hist)
+    assert (st["episodes"], st["score_sum"], st["step_sum"], st["score_max"]) == (episodes, score_sum, step_sum, score_max)
+    assert episodes > 1000
+
+
+def test_step_random_picks_valid_actions_uniformly(ml):
+    m = 1 << 16
+    env = _make(ml, m, output="torch")
+    env.reset(3)
+    counts = np.zeros((5, 4), np.int64)  # by number of valid actions
+    for _ in range(60):
+        env.prepare()
+        valid = env.observations()[1].clone()
+        res = env.step_random(return_actions=True)
+        acts = env._actions_out.long()
+        assert not res["invalid"].any(), "a random VALID action can never be an invalid move"
+        assert valid.gather(1, acts[:, None]).all()
+        nv = valid.sum(dim=1)
+        sel = nv == 2
+        first = valid[sel].float().argmax(dim=1)
+        counts[2, 0] += int((acts[sel] == first).sum())
+        counts[2, 1] += int((acts[sel] != first).sum())
+    frac = counts[2, 0] / counts[2].sum()
+    assert abs(frac - 0.5) < 0.01, frac
+
+
+def test_philox_mode_statistics(ml):
+    """Philox spawns have no bit-exact counterpart; they must reproduce the reference's random-policy
+    episode statistics (M=8192, 1200 steps: mean 107.5 valid steps/episode, mean
+    final score 1023, max-tile histogram {3:3, 4:274, 5:6851, 6:34881, 7:39444, 8:5789, 9:8})."""
+    ref_hist = np.zeros(20)
+    for k, v in {3: 3, 4: 274, 5: 6851, 6: 34881, 7: 39444, 8: 5789, 9: 8}.items():
+        ref_hist[k] = v
+    env = _make(ml, 8192, rng_mode="philox", output="torch", sync_free=True, track_merged=False)
+    env.reset(2024)
+    for _ in range(1200):
+        env.prepare()
+        env.step_random()
+    st = env.episode_stats()
+    assert 80000 < st["episodes"] < 95000
+    assert abs(st["mean_steps"] - 107.5) < 1.5, st["mean_steps"]
+    assert abs(st["mean_score"] - 1023) < 25, st["mean_score"]
+    p_ref = ref_hist / ref_hist.sum()
+    p_got = st["max_tile_hist"] / st["max_tile_hist"].sum()
+    assert np.abs(p_ref - p_got).max() < 0.01, (p_ref, p_got)
+
+
+def test_philox_is_deterministic_and_shard_invariant(ml):
+    """Same seed -> same boards; and splitting the games over two shards (slot_base) changes nothing."""
+    m = 6000
+    whole = _make(ml, m, rng_mode="philox", output="torch")
+    lo = _make(ml, 2500, rng_mode="philox", output="torch", slot_base=0)
+    hi = _make(ml, m - 2500, rng_mode="philox", output="torch", slot_base=2500)
+    for e in (whole, lo, hi):
+        e.reset(99)
+    for _ in range(150):
+        for e in (whole, lo, hi):
+            e.prepare()
+            e.step_random()
+    got = torch.cat([lo.observations()[0], hi.observations()[0]])
+    assert torch.equal(got, whole.observations()[0])
+    assert torch.equal(torch.cat([lo._score, hi._score]), whole._score)
+    again = _make(ml, m, rng_mode="philox", output="torch")
+    again.reset(99)
+    for _ in range(150):
+        again.prepare()
+        again.step_random()
+    assert torch.equal(again.observations()[0], whole.observations()[0])
+
+
+def test_replay_mode_is_shard_invariant(ml):
+    """Replay tables are indexed by the GLOBAL slot (game_numba.py:651, :733), so a sharded run equals
+    the single-shard run slot for slot."""
+    m = 5000
+    whole = _make(ml, m)
+    lo = _make(ml, 1234, slot_base=0)
+    hi = _make(ml, m - 1234, slot_base=1234)
+    for e in (whole, lo, hi):
+        e.reset(31)
+    rng = np.random.default_rng(2)
+    for _ in range(120):
+        for e in (whole, lo, hi):
+            e.prepare()
+        valid = whole.observations()[1]
+        u = rng.random(m)
+        nv = valid.astype(bool).sum(axis=1)
+        k = np.minimum((u * nv).astype(np.int64), np.maximum(nv - 1, 0))
+        rank = np.cumsum(valid.astype(bool), axis=1) - 1
+        acts = np.where(nv > 0, (valid.astype(bool) & (rank == k[:, None])).argmax(axis=1), 0).astype(np.int64)
+        whole.step(acts)
+        lo.step(acts[:1234])
+        hi.step(acts[1234:])
+    got = np.concatenate([lo.observations()[0], hi.observations()[0]])
+    np.testing.assert_array_equal(got, whole.observations()[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at the benchmark size
+# ---------------------------------------------------------------------------------------------
+
+
+def test_properties_at_bench_size(ml):
+    """M = 2^24 (BASELINE config 3/4 per-GPU size): conservation laws that hold for every game.
+       tiles: sum(2^cell) grows by exactly the spawned tile (2 or 4) on a valid move, 0 otherwise;
+       score: grows by exactly `reward` (normal reward);  one-hot: every cell has exactly one class;
+       mask: valid_actions == 0 <=> terminated;  idempotence: an invalid move changes nothing."""
+    m = 1 << 24
+    env = _make(ml, m, rng_mode="philox", output="torch", onehot="u8", sync_free=True, track_merged=False)
+    env.reset(1)
+
+    def tile_sum(board):
+        return torch.where(board > 0, torch.ones((), dtype=torch.int64, device=board.device) << board.long(), 0).sum(dim=1)
+
+    for t in range(24):
+        env.prepare()
+        before = env.observations()[0]
+        s_before = tile_sum(before)
+        score_before = env._score.clone()
+        res = env.step_random()
+        after = res["state"]
+        grown = tile_sum(after) - s_before
+        moved = res["invalid"] == 0
+        assert bool(((grown == 2) | (grown == 4))[moved].all())
+        assert bool((grown == 0)[~moved].all())
+        assert torch.equal(env._score - score_before, torch.where(moved, env._reward, torch.zeros_like(env._reward)))
+        assert torch.equal(res["valid_actions"].sum(dim=1) == 0, res["terminated"] != 0)
+    oh = env.observations_onehot()
+    assert bool((oh.sum(dim=1) == 1).all())
+    # idempotence of invalid moves: push every game in a direction its mask forbids (if any)
+    env.prepare()
+    board, valid = env.observations()
+    board, valid = board.clone(), valid.clone()
+    bad = (valid == 0).float().argmax(dim=1)
+    has_bad = (valid == 0).any(dim=1)
+    score = env._score.clone()
+    res = env.step(bad)
+    assert torch.equal(res["invalid"] != 0, has_bad)
+    assert torch.equal(res["state"][has_bad], board[has_bad])
+    assert torch.equal(env._score[has_bad], score[has_bad])
