@@ -13,6 +13,15 @@ namespace ml2048 {
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 
+// PRMT in its generic PTX form: a selector nibble with bit 3 set replicates the SIGN of the selected byte
+// over the whole result byte (__byte_perm masks that bit away, so this needs inline PTX).
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+
 constexpr uint32_t kHi = 0x80808080u;
 constexpr uint32_t kLo7 = 0x7f7f7f7fu;
 
@@ -171,7 +180,7 @@ __device__ __forceinline__ uint32_t first_empty_in_order(uint4 perm, uint32_t z0
         const uint32_t sel = prmt(s, 0u, 0x4420);    // selector nibbles (p0,p1,p2,p3) mod 8
         const uint32_t lo = prmt(z0, z1, sel);       // cells 0..7
         const uint32_t hi = prmt(z2, z3, sel);       // cells 8..15
-        const uint32_t up = prmt(p << 4, 0u, 0xba98);  // 0xff where p >= 8
+        const uint32_t up = prmt_sign(p << 4, 0u, 0xba98);  // 0xff where p >= 8
         hit[i] = (lo & ~up) | (hi & up);
     }
     uint32_t h = hit[0], p = pw[0];

@@ -47,10 +47,10 @@ struct OneHotPiece<ML2048_ONEHOT_F32> {  // 4 cells -> 4 floats = 16 bytes; 64 p
         const uint32_t word = reinterpret_cast<const uint32_t *>(boards + game)[piece & 3];
         const uint32_t eq = (((word ^ (k * 0x01010101u)) + kLo7) & kHi) ^ kHi;  // 0x80 where cell == k
         float4 v;
-        v.x = __uint_as_float(prmt(eq, 0u, 0x8888) & 0x3f800000u);
-        v.y = __uint_as_float(prmt(eq, 0u, 0x9999) & 0x3f800000u);
-        v.z = __uint_as_float(prmt(eq, 0u, 0xaaaa) & 0x3f800000u);
-        v.w = __uint_as_float(prmt(eq, 0u, 0xbbbb) & 0x3f800000u);
+        v.x = __uint_as_float(prmt_sign(eq, 0u, 0x8888) & 0x3f800000u);
+        v.y = __uint_as_float(prmt_sign(eq, 0u, 0x9999) & 0x3f800000u);
+        v.z = __uint_as_float(prmt_sign(eq, 0u, 0xaaaa) & 0x3f800000u);
+        v.w = __uint_as_float(prmt_sign(eq, 0u, 0xbbbb) & 0x3f800000u);
         return v;
     }
 };
@@ -61,7 +61,7 @@ struct OneHotPiece<ML2048_ONEHOT_BF16> {  // 8 cells -> 8 bf16 = 16 bytes; 32 pi
     static constexpr int kPiecesPerGame = 32;
     static __device__ __forceinline__ uint32_t pair(uint32_t eq, uint32_t sel)
     {
-        return prmt(eq, 0u, sel) & 0x3f803f80u;  // two bf16 1.0 (0x3f80) where the cells matched
+        return prmt_sign(eq, 0u, sel) & 0x3f803f80u;  // two bf16 1.0 (0x3f80) where the cells matched
     }
     static __device__ __forceinline__ vec make(const uint4 *boards, int game, int piece)
     {

@@ -497,6 +497,64 @@ class VecGame:
         code = {torch.int64: _lib.ACT_I64, torch.int32: _lib.ACT_I32, torch.uint8: _lib.ACT_U8, torch.int8: _lib.ACT_U8}
         return actions, code[actions.dtype]
 
+    def configure(self, *, output: Optional[str] = None, sync_free: Optional[bool] = None) -> None:
+        """Switch between host (NumPy) and device (torch) results, or the sync-free prepare(), on a live environment."""
+        if output is not None:
+            if output not in ("numpy", "torch"):
+                raise ValueError(f"output={output!r}")
+            self._output = output
+        if sync_free is not None:
+            self._sync_free = bool(sync_free)
+
+    def state_dict(self) -> dict[str, Any]:
+        """Snapshot of the whole environment (device tensors are cloned, host random schedule copied).
+        The reference never checkpoints the environment; this makes rollouts
+        restartable and lets a benchmark replay a recorded trajectory."""
+        import copy
+
+        torch.cuda.current_stream(self.device).synchronize()
+        tensors = {
+            name: getattr(self, name).clone()
+            for name in ("_board", "_valid", "_id", "_step", "_score", "_reward", "_terminated_padded", "_invalid",
+                         "_randperm_dev", "_game_count_dev", "_stats_dev")
+        }
+        if self._merged is not None:
+            tensors["_merged"] = self._merged.clone()
+        if self._onehot is not None:
+            tensors["_onehot"] = self._onehot.clone()
+        host = {
+            "size": self._size,
+            "cur": self._cur,
+            "rand_step": self._rand_step,
+            "randperm": self._randperm.copy(),
+            "randfloat": self._randfloat.copy(),
+            "two_mask": self._two_mask,
+            "philox_seed": self._philox_seed,
+            "philox_counter": self._philox_counter,
+            "schedule": copy.deepcopy(self._schedule),
+        }
+        return {"tensors": tensors, "host": host}
+
+    def load_state_dict(self, sd: dict[str, Any]) -> None:
+        import copy
+
+        host = sd["host"]
+        if host["size"] != self._size:
+            raise ValueError(f"snapshot holds {host['size']} games, this environment {self._size}")
+        for name, t in sd["tensors"].items():
+            dst = getattr(self, name)
+            if dst is None:
+                raise ValueError(f"snapshot has {name} but this environment does not track it")
+            dst.copy_(t)
+        self._cur = host["cur"]
+        self._rand_step = host["rand_step"]
+        self._randperm[...] = host["randperm"]
+        self._randfloat[...] = host["randfloat"]
+        self._two_mask = host["two_mask"]
+        self._philox_seed = host["philox_seed"]
+        self._philox_counter = host["philox_counter"]
+        self._schedule = copy.deepcopy(host["schedule"])
+
     def episode_stats(self, *, reset: bool = False) -> dict[str, Any]:
         """Finished-episode statistics accumulated by step(): RunnerStats' max-tile histogram
         (runner.py:150-166) plus episode count, score and step sums, max score."""

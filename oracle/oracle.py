@@ -89,6 +89,8 @@ def load_lib() -> ctypes.CDLL:
     lib.orc_line_flags.restype = None
     lib.orc_board_spawn.argtypes = [vp, vp, i64, i64, vp, dbl, i32]
     lib.orc_board_spawn.restype = i32
+    lib.orc_random_valid_actions.argtypes = [vp, i64, c.c_uint64, vp]
+    lib.orc_random_valid_actions.restype = None
     lib.orc_num_threads.argtypes = []
     lib.orc_num_threads.restype = i32
     lib.orc_set_num_threads.argtypes = [i32]
@@ -311,6 +313,13 @@ class OracleVecGame:
         entries = [(2 ** int(k), int(counts[k]), counts[k] / total) for k in range(20) if counts[k]]
         entries.sort(key=lambda s: s[0], reverse=True)
         return entries
+
+    def random_valid_actions(self, seed: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Uniform-over-valid actions for every game (benchmark policy), computed in C."""
+        if out is None:
+            out = np.empty((self._size,), dtype=np.int64)
+        self._lib.orc_random_valid_actions(_ptr(self._data), self._size, seed & 0xFFFFFFFFFFFFFFFF, _ptr(out))
+        return out
 
     # -- adjacent statistic (RunnerStats, runner.py:120-166) ----------------------------------
 
