@@ -50,13 +50,14 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--cpu-games", type=int, default=1 << 22, help="games per CPU step (bounded sample)")
+    p.add_argument("--burn-in", type=int, default=BURN_IN, help="untimed steps from reset() to steady state")
     return p.parse_args()
 
 
-def workload_name(games_per_gpu: int) -> str:
+def workload_name(games_per_gpu: int, burn_in: int = BURN_IN) -> str:
     return (f"random-valid-action rollout, M={games_per_gpu} games/GPU (2^{games_per_gpu.bit_length() - 1}), "
             "prepare(auto-reset)+step+spawn+mask+terminal fused with fp32 one-hot obs, replay (bit-exact) tables, "
-            f"steady state after {BURN_IN}-step burn-in")
+            f"steady state after {burn_in}-step burn-in")
 
 
 # -------------------------------------------------------------------------------------------------
@@ -141,7 +142,7 @@ def run_reference_arm(args: argparse.Namespace) -> None:
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU every 100 ms through NVML while running."""
+    """Samples SM clock and throttle reasons of one GPU every 10 ms through NVML while running."""
 
     REASONS = {
         0x8: "hw_slowdown",
@@ -191,7 +192,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.01)
 
     def stop(self) -> dict:
         self._halt.set()
@@ -266,7 +267,7 @@ def run_b200_arm(args: argparse.Namespace) -> None:
     env = ml2048_b200.VecGame(m, ml2048_b200.reward_fn_normal, output="torch", onehot="f32", track_merged=False,
                               slot_base=slot_base, sync_free=True, device=dev)
     env.reset(args.seed)
-    for _ in range(BURN_IN):
+    for _ in range(args.burn_in):
         env.prepare()
         env.step_random()
     torch.cuda.synchronize()
@@ -391,7 +392,7 @@ def run_b200_arm(args: argparse.Namespace) -> None:
             "dtype": "u8",
             "data": "synthetic",
             "config": {
-                "workload": workload_name(m),
+                "workload": workload_name(m, args.burn_in),
                 "games_per_gpu": m,
                 "global_games": m * world,
                 "sharding": f"dp{world}: contiguous global slots, no data-path collective; 1 all-reduce of 24 ints for statistics",
