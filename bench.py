@@ -71,6 +71,12 @@ def time_cpu_port(games: int, steps: int, warmup: int, seed: int, budget_s: floa
     from oracle import oracle as orc
 
     lib = orc.load_lib()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it for the CPU arm)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    lib.orc_set_num_threads(avail)
     cores = int(lib.orc_num_threads())
     env = orc.OracleVecGame(games, "normal")
     env.reset(seed)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ML2048_ABI_VERSION 1
+#define ML2048_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ML2048_API __attribute__((visibility("default")))
@@ -106,7 +106,8 @@ typedef struct {
     void *onehot_out;      /* [num_games][16][16] of onehot_dtype, or null */
 
     /* replay mode (game_numba.py:733, 172-212) */
-    const uint8_t *randperm; /* [1024][16] permutations of 0..15 */
+    const uint8_t *randperm_keys; /* [1024][16]: the reference's randperm table in inverse form,
+                                     keys[row][cell] = 16*rank(cell)+cell (ml2048_pack_randperm_keys) */
     int64_t rand_seed;       /* _rand_step + rand_offset (:681); row = (rand_seed + global slot) mod 1024 */
     uint32_t two_mask;       /* bit c set <=> (double)randfloat[c] < two_prob (see ml2048_two_mask) */
 
@@ -196,6 +197,9 @@ ML2048_API int ml2048_sample_random_valid(const void *valid, uint8_t *actions_ou
 /* host helpers (no GPU work) */
 ML2048_API uint32_t ml2048_two_mask(const float *host_randfloat16, double two_prob);   /* game_numba.py:207 (f32 -> f64 compare) */
 ML2048_API uint32_t ml2048_two_threshold(double two_prob);
+/* randperm (u8 [rows][16], each row a permutation of 0..15, game_numba.py:578,610) -> inverse-form keys used by
+ * ml2048_step: the kernel picks the empty cell of smallest rank = the first empty cell of the table walk (:198-204) */
+ML2048_API int ml2048_pack_randperm_keys(const uint8_t *host_randperm, uint8_t *host_keys, int64_t rows);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libml2048_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 STATS_REPLICAS = 64
 STATS_WORDS = 24  # 20 histogram bins + episodes, score_sum, step_sum, score_max (unsigned long long each)
 
@@ -50,7 +50,7 @@ class StepArgs(C.Structure):
         ("invalid", C.c_void_p),
         ("merged", C.c_void_p),
         ("onehot_out", C.c_void_p),
-        ("randperm", C.c_void_p),
+        ("randperm_keys", C.c_void_p),
         ("rand_seed", C.c_int64),
         ("two_mask", C.c_uint32),
         ("two_threshold", C.c_uint32),
@@ -110,6 +110,7 @@ SYMBOLS = {
     "ml2048_sample_random_valid": (C.c_int, [_VP, _VP, _I64, _I64, _U64, _U64, _VP]),
     "ml2048_two_mask": (_U32, [_VP, C.c_double]),
     "ml2048_two_threshold": (_U32, [C.c_double]),
+    "ml2048_pack_randperm_keys": (C.c_int, [_VP, _VP, _I64]),
 }
 
 _lib = None

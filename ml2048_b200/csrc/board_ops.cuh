@@ -3,86 +3,164 @@
 // A board is four 32-bit words (one per row), one byte per cell holding the tile exponent
 // (0 = empty), cell = row*4+col with column 0 in the least significant byte -- i.e. exactly the 16
 // bytes of the reference's `board` field read as a little-endian uint4 (game_numba.py:13-20, :542).
-// Everything here is branch-free byte-SWAR on those four words: PRMT (__byte_perm) for the data
-// movement, carry-free adds for the per-byte zero tests (cell values are <= 17, so `byte + 0x7f`
-// never carries into the next byte).  No local memory, no lookup tables.
+//
+// Everything here is branch-free byte-SWAR on those words.  The move works "lane-parallel": the four
+// lines that a move pushes are held as four words A,B,C,D where byte lane i belongs to line i and A is
+// the cell next to the wall, so ONE sequence of 32-bit logic ops pushes all four lines at once.
+// PRMT does the data movement (4x4 byte transpose) and, in its sign-replicating form, turns per-byte
+// flags into full-byte masks; per-byte zero tests are carry-free adds (cells are <= 17 and xors of
+// cells <= 31, so `byte + 0x7f` never carries into the next byte).  No local memory, no lookup tables.
+//
+// The header also compiles as plain C++ (tests/host_shim) so the arithmetic can be checked exhaustively
+// against the CPU oracle without a GPU; the #else branch below emulates the four intrinsics it uses.
 #pragma once
 #include <stdint.h>
 
+#if defined(__CUDACC__)
+#define ML2048_FN __device__ __forceinline__
+#else
+#define ML2048_FN static inline
+#endif
+
 namespace ml2048 {
 
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+#if defined(__CUDACC__)
+ML2048_FN uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 
 // PRMT in its generic PTX form: a selector nibble with bit 3 set replicates the SIGN of the selected byte
 // over the whole result byte (__byte_perm masks that bit away, so this needs inline PTX).
-__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t b, uint32_t s)
+ML2048_FN uint32_t prmt_sign(uint32_t a, uint32_t b, uint32_t s)
 {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
     return d;
 }
+ML2048_FN uint32_t popc32(uint32_t x) { return (uint32_t)__popc(x); }
+ML2048_FN uint32_t ffs32(uint32_t x) { return (uint32_t)__ffs((int)x); }
+ML2048_FN uint32_t umulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// min over three pairs of unsigned 16-bit lanes (DPX, one instruction on sm_90+)
+ML2048_FN uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+#else
+ML2048_FN uint32_t prmt_sign(uint32_t a, uint32_t b, uint32_t s)
+{
+    const uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t d = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t sel = (s >> (4 * i)) & 0xfu;
+        uint32_t byte = (uint32_t)(pool >> (8 * (sel & 7u))) & 0xffu;
+        if (sel & 8u) byte = (byte & 0x80u) ? 0xffu : 0x00u;
+        d |= byte << (8 * i);
+    }
+    return d;
+}
+ML2048_FN uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return prmt_sign(a, b, s & 0x7777u); }
+ML2048_FN uint32_t popc32(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+ML2048_FN uint32_t ffs32(uint32_t x) { return (uint32_t)__builtin_ffs((int)x); }
+ML2048_FN uint32_t umulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+ML2048_FN uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+    auto mn = [](uint32_t x, uint32_t y) { return x < y ? x : y; };
+    const uint32_t lo = mn(mn(a & 0xffffu, b & 0xffffu), c & 0xffffu);
+    const uint32_t hi = mn(mn(a >> 16, b >> 16), c >> 16);
+    return lo | (hi << 16);
+}
+#endif
 
 constexpr uint32_t kHi = 0x80808080u;
 constexpr uint32_t kLo7 = 0x7f7f7f7fu;
+constexpr uint32_t kOnes = 0x01010101u;
 
 // 0x80 in every byte whose cell is non-empty
-__device__ __forceinline__ uint32_t occupied_flags(uint32_t row) { return (row + kLo7) & kHi; }
+ML2048_FN uint32_t occupied_flags(uint32_t row) { return (row + kLo7) & kHi; }
 
-// What one move fused.  `gain` is the reference's reward_fn_normal (game_numba.py:408-438),
-// `rank` reward_fn_rank (:469-484), `count` the merged.sum() of reward_fn_maxcell (:502), and
-// `log` the `merged` array itself as sixteen 4-bit counters (at most 8 fusions per move).
+// 0xff in every byte of x that is non-zero (bytes of x must be <= 0x80)
+ML2048_FN uint32_t nonzero_mask(uint32_t x) { return prmt_sign(x + kLo7, 0u, 0xba98); }
+
+// What one move fused: `first`/`second` hold the exponents of the consumed tiles, one byte per line
+// (0 = no fusion); a line fuses at most twice.  From them: the reference's reward_fn_normal
+// (game_numba.py:408-438), reward_fn_rank (:469-484), the merged.sum() of reward_fn_maxcell (:502)
+// and the `merged` array itself.
 struct Fusions {
-    uint32_t gain;
-    uint32_t rank;
-    uint32_t count;
-    unsigned long long log;
+    uint32_t first;
+    uint32_t second;
+    uint32_t count;  // number of fusions of the move (<= 8)
 };
 
-template <bool kLog>
-__device__ __forceinline__ void note_fusion(Fusions &f, uint32_t k)
+// Four lines pushed toward A at once.  Same result per line as the reference's _push_row
+// (game_numba.py:48-90): stable compaction of the tiles, then equal neighbours fuse once, in order
+// from the wall, a fused tile never fusing again.
+ML2048_FN void push4(uint32_t &A, uint32_t &B, uint32_t &C, uint32_t &D, Fusions &f)
 {
-    f.gain += 2u << k;  // two tiles of exponent k became one tile worth 2^(k+1)
-    f.rank += k + 1u;
-    f.count += 1u;
-    if (kLog) {
-        if (k < 16u)  // merged[] has 16 slots (game_numba.py:543); tile 65536 is never reached
-            f.log += 1ull << (4u * k);
-    }
+    // stable compaction: close the gap at position C, then B, then A
+    uint32_t m;
+    m = nonzero_mask(C);
+    C = C | (D & ~m);
+    D = D & m;
+    m = nonzero_mask(B);
+    B = B | (C & ~m);
+    C = (C & m) | (D & ~m);
+    D = D & m;
+    m = nonzero_mask(A);
+    A = A | (B & ~m);
+    B = (B & m) | (C & ~m);
+    C = (C & m) | (D & ~m);
+    D = D & m;
+    // which neighbours fuse (full-byte masks): a/b first, then b/c unless b was used, then c/d unless c was used
+    const uint32_t eab = ~nonzero_mask(A ^ B) & nonzero_mask(A);
+    const uint32_t ebc = ~nonzero_mask(B ^ C) & nonzero_mask(B) & ~eab;
+    const uint32_t ecd = ~nonzero_mask(C ^ D) & nonzero_mask(C) & ~ebc;
+    f.first = (A & eab) | (B & ebc) | (C & ecd & ~eab);  // per line these three exclude each other
+    f.second = C & ecd & eab;
+    f.count = (popc32(eab | ebc) + popc32(ecd)) >> 3;
+    const uint32_t both = eab & ecd;    // [a+1, c+1, 0, 0]
+    const uint32_t shift = eab | ebc;   // position C receives D
+    const uint32_t nA = A + (eab & kOnes);
+    const uint32_t nB = ((C & eab) | (B & ~eab)) + ((ebc | both) & kOnes);
+    const uint32_t nC = (D & shift & ~both) | ((C + (ecd & kOnes)) & ~shift);
+    const uint32_t nD = D & ~(shift | ecd);
+    A = nA, B = nB, C = nC, D = nD;
 }
 
-// One line of four cells pushed toward byte 0.  Same result as the reference's _push_row
-// (game_numba.py:48-90): stable compaction of the tiles, then equal neighbours fuse once, in
-// order from the wall, a fused tile never fusing again.
-template <bool kLog>
-__device__ __forceinline__ uint32_t push_line(uint32_t w, Fusions &f)
+// sum over the (up to 8) fusions of 2^(k+1): the reference's reward_fn_normal
+ML2048_FN uint32_t fusion_gain(const Fusions &f)
 {
-    // stable compaction: close the gap at byte 2, then 1, then 0
-    if ((w & 0x00ff0000u) == 0u) w = prmt(w, 0u, 0x4310);
-    if ((w & 0x0000ff00u) == 0u) w = prmt(w, 0u, 0x4320);
-    if ((w & 0x000000ffu) == 0u) w = prmt(w, 0u, 0x4321);
-    // compacted cells a,b,c,d : x holds a^b, b^c, c^d, d
-    const uint32_t x = w ^ (w >> 8);
-    const bool ab = ((x & 0x000000ffu) == 0u) && ((w & 0x000000ffu) != 0u);
-    const bool bc = ((x & 0x0000ff00u) == 0u) && ((w & 0x0000ff00u) != 0u) && !ab;
-    const bool cd = ((x & 0x00ff0000u) == 0u) && ((w & 0x00ff0000u) != 0u) && !bc;
-    const uint32_t a = w & 0xffu, b = (w >> 8) & 0xffu, c = (w >> 16) & 0xffu;
-    if (ab) {
-        note_fusion<kLog>(f, a);
-        w = prmt(w, 0u, 0x4320) + 0x00000001u;  // [a+1, c, d, 0]
-    }
-    if (bc) {
-        note_fusion<kLog>(f, b);
-        w = prmt(w, 0u, 0x4310) + 0x00000100u;  // [a, b+1, d, 0]
-    }
-    if (cd) {
-        note_fusion<kLog>(f, c);
-        // after an a/b fusion the pair sits in bytes 1,2: [a+1, c+1, 0, 0]; otherwise [a, b, c+1, 0]
-        w = ab ? ((w & 0x0000ffffu) + 0x00000100u) : ((w & 0x00ffffffu) + 0x00010000u);
-    }
-    return w;
+    // 1<<k for all eight candidate bytes; an empty candidate (k = 0) adds 1, removed afterwards
+    uint32_t s = (1u << (f.first & 0xffu)) + (1u << prmt(f.first, 0u, 0x4441)) + (1u << prmt(f.first, 0u, 0x4442)) +
+                 (1u << (f.first >> 24));
+    s += (1u << (f.second & 0xffu)) + (1u << prmt(f.second, 0u, 0x4441)) + (1u << prmt(f.second, 0u, 0x4442)) +
+         (1u << (f.second >> 24));
+    return (s - 8u + f.count) << 1;
 }
 
-__device__ __forceinline__ void transpose4x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3)
+// sum over the fusions of (k+1): reward_fn_rank
+ML2048_FN uint32_t fusion_rank(const Fusions &f)
+{
+    return (((f.first + f.second) * kOnes) >> 24) + f.count;
+}
+
+// the reference's `merged` u8[16] as four words: merged[k] = number of fusions that consumed exponent k.
+// Exponents >= 16 have no slot (game_numba.py:543; the reference would index out of bounds) and are dropped.
+ML2048_FN void fusion_log(const Fusions &f, uint32_t &m0, uint32_t &m1, uint32_t &m2, uint32_t &m3)
+{
+    unsigned long long nib = 0ull;  // sixteen 4-bit counters
+    const uint32_t w[2] = {f.first, f.second};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t k = (w[i] >> (8 * j)) & 0xffu;
+            if (k != 0u && k < 16u) nib += 1ull << (4u * k);
+        }
+    }
+    const uint32_t lo = (uint32_t)nib, hi = (uint32_t)(nib >> 32);
+    m0 = lo & 0xffffu, m1 = lo >> 16, m2 = hi & 0xffffu, m3 = hi >> 16;
+    m0 = (m0 | (m0 << 8)) & 0x00ff00ffu; m0 = (m0 | (m0 << 4)) & 0x0f0f0f0fu;
+    m1 = (m1 | (m1 << 8)) & 0x00ff00ffu; m1 = (m1 | (m1 << 4)) & 0x0f0f0f0fu;
+    m2 = (m2 | (m2 << 8)) & 0x00ff00ffu; m2 = (m2 | (m2 << 4)) & 0x0f0f0f0fu;
+    m3 = (m3 | (m3 << 8)) & 0x00ff00ffu; m3 = (m3 | (m3 << 4)) & 0x0f0f0f0fu;
+}
+
+ML2048_FN void transpose4x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3)
 {
     const uint32_t t0 = prmt(r0, r1, 0x5140);  // r0.0 r1.0 r0.1 r1.1
     const uint32_t t1 = prmt(r2, r3, 0x5140);
@@ -95,29 +173,24 @@ __device__ __forceinline__ void transpose4x4(uint32_t &r0, uint32_t &r1, uint32_
 }
 
 // The move itself: direction dispatch of _step_kernel (game_numba.py:93-134) without a branch.
-// action bit 1 = vertical (work on the transposed board), bit 0 = toward the high end (reverse lines).
-template <bool kLog>
-__device__ __forceinline__ void move_board(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t action,
-                                           Fusions &f)
+// action bit 1 = vertical (lines are columns: the rows already are the lane-parallel words),
+// bit 0 = toward the high end (the wall is at the other end: A..D are taken in reverse order).
+ML2048_FN void move_board(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t action, Fusions &f)
 {
     const bool vertical = (action & 2u) != 0u;
-    const uint32_t flip = (action & 1u) ? 0x0123u : 0x3210u;
+    const bool reverse = (action & 1u) != 0u;
     uint32_t c0 = r0, c1 = r1, c2 = r2, c3 = r3;
     transpose4x4(c0, c1, c2, c3);
-    uint32_t l0 = prmt(vertical ? c0 : r0, 0u, flip);
-    uint32_t l1 = prmt(vertical ? c1 : r1, 0u, flip);
-    uint32_t l2 = prmt(vertical ? c2 : r2, 0u, flip);
-    uint32_t l3 = prmt(vertical ? c3 : r3, 0u, flip);
-    l0 = prmt(push_line<kLog>(l0, f), 0u, flip);
-    l1 = prmt(push_line<kLog>(l1, f), 0u, flip);
-    l2 = prmt(push_line<kLog>(l2, f), 0u, flip);
-    l3 = prmt(push_line<kLog>(l3, f), 0u, flip);
-    c0 = l0, c1 = l1, c2 = l2, c3 = l3;
+    const uint32_t x0 = vertical ? r0 : c0, x1 = vertical ? r1 : c1, x2 = vertical ? r2 : c2, x3 = vertical ? r3 : c3;
+    uint32_t A = reverse ? x3 : x0, B = reverse ? x2 : x1, C = reverse ? x1 : x2, D = reverse ? x0 : x3;
+    push4(A, B, C, D, f);
+    const uint32_t y0 = reverse ? D : A, y1 = reverse ? C : B, y2 = reverse ? B : C, y3 = reverse ? A : D;
+    c0 = y0, c1 = y1, c2 = y2, c3 = y3;
     transpose4x4(c0, c1, c2, c3);
-    r0 = vertical ? c0 : l0;
-    r1 = vertical ? c1 : l1;
-    r2 = vertical ? c2 : l2;
-    r3 = vertical ? c3 : l3;
+    r0 = vertical ? y0 : c0;
+    r1 = vertical ? y1 : c1;
+    r2 = vertical ? y2 : c2;
+    r3 = vertical ? y3 : c3;
 }
 
 // Valid-action mask, one byte per direction (left,right,up,down), as the little-endian word the
@@ -125,36 +198,28 @@ __device__ __forceinline__ void move_board(uint32_t &r0, uint32_t &r1, uint32_t 
 // can slide into an empty cell or fuse with its neighbour on that axis -- the predicate
 // _line_movable (:215-256) enumerates pairwise, proven equal to "the move changes the board" for
 // all 18^4 lines (tests/test_oracle_golden.py::test_line_table_exhaustive).
-__device__ __forceinline__ uint32_t valid_mask(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+//   slide toward a wall  <=>  some tile has an EMPTY neighbour on the wall side
+//   fuse on an axis      <=>  some tile equals its neighbour on that axis
+ML2048_FN uint32_t valid_mask(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
 {
     const uint32_t n0 = occupied_flags(r0), n1 = occupied_flags(r1), n2 = occupied_flags(r2), n3 = occupied_flags(r3);
-    const uint32_t z0 = n0 ^ kHi, z1 = n1 ^ kHi, z2 = n2 ^ kHi, z3 = n3 ^ kHi;
-    // slides along rows: an empty cell with a tile further from the wall
-    uint32_t s, left, right;
-    s = z0 | (z0 << 8); left = (s | (s << 16)) & n0;
-    s = z1 | (z1 << 8); left |= (s | (s << 16)) & n1;
-    s = z2 | (z2 << 8); left |= (s | (s << 16)) & n2;
-    s = z3 | (z3 << 8); left |= (s | (s << 16)) & n3;
-    s = z0 | (z0 >> 8); right = (s | (s >> 16)) & n0;
-    s = z1 | (z1 >> 8); right |= (s | (s >> 16)) & n1;
-    s = z2 | (z2 >> 8); right |= (s | (s >> 16)) & n2;
-    s = z3 | (z3 >> 8); right |= (s | (s >> 16)) & n3;
-    // slides along columns
-    const uint32_t up = (z0 & (n1 | n2 | n3)) | (z1 & (n2 | n3)) | (z2 & n3);
-    const uint32_t down = (z3 & (n0 | n1 | n2)) | (z2 & (n0 | n1)) | (z1 & n0);
-    // fusions: equal neighbours where the first one is a tile (0x20 marks empty cells so they never match)
-    const uint32_t q0 = z0 >> 2, q1 = z1 >> 2, q2 = z2 >> 2, q3 = z3 >> 2;
-    const uint32_t hz = ((((r0 ^ (r0 >> 8)) | q0) + kLo7) & (((r1 ^ (r1 >> 8)) | q1) + kLo7) &
-                         (((r2 ^ (r2 >> 8)) | q2) + kLo7) & (((r3 ^ (r3 >> 8)) | q3) + kLo7)) & kHi;
-    const uint32_t vt = ((((r0 ^ r1) | q0) + kLo7) & (((r1 ^ r2) | q1) + kLo7) & (((r2 ^ r3) | q2) + kLo7)) & kHi;
-    const bool hfuse = hz != kHi, vfuse = vt != kHi;
-    const uint32_t l = (left != 0u) || hfuse, r = (right != 0u) || hfuse;
-    const uint32_t u = (up != 0u) || vfuse, d = (down != 0u) || vfuse;
+    // rows: byte j+1 occupied and byte j empty -> can slide left; byte j-1 occupied and byte j empty -> right
+    const uint32_t left = ((n0 >> 8) & ~n0) | ((n1 >> 8) & ~n1) | ((n2 >> 8) & ~n2) | ((n3 >> 8) & ~n3);
+    const uint32_t right = ((n0 << 8) & ~n0) | ((n1 << 8) & ~n1) | ((n2 << 8) & ~n2) | ((n3 << 8) & ~n3);
+    // columns: row i+1 occupied above an empty row i -> up; the other way -> down
+    const uint32_t up = (n1 & ~n0) | (n2 & ~n1) | (n3 & ~n2);
+    const uint32_t down = (n0 & ~n1) | (n1 & ~n2) | (n2 & ~n3);
+    // fusions: xor of neighbours is zero where the first one is a tile (byte 3 of a row xor is the cell itself)
+    const uint32_t hfuse = (~((r0 ^ (r0 >> 8)) + kLo7) & n0) | (~((r1 ^ (r1 >> 8)) + kLo7) & n1) |
+                           (~((r2 ^ (r2 >> 8)) + kLo7) & n2) | (~((r3 ^ (r3 >> 8)) + kLo7) & n3);
+    const uint32_t vfuse = (~((r0 ^ r1) + kLo7) & n0) | (~((r1 ^ r2) + kLo7) & n1) | (~((r2 ^ r3) + kLo7) & n2);
+    const uint32_t l = ((left | hfuse) & kHi) != 0u, r = ((right | hfuse) & kHi) != 0u;
+    const uint32_t u = ((up | vfuse) & kHi) != 0u, d = ((down | vfuse) & kHi) != 0u;
     return l | (r << 8) | (u << 16) | (d << 24);
 }
 
 // Write `value` into cell `cell` (0..15) of the board.
-__device__ __forceinline__ void put_cell(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t cell, uint32_t value)
+ML2048_FN void put_cell(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t cell, uint32_t value)
 {
     const uint32_t v = value << ((cell & 3u) * 8u);
     const uint32_t row = cell >> 2;
@@ -164,78 +229,85 @@ __device__ __forceinline__ void put_cell(uint32_t &r0, uint32_t &r1, uint32_t &r
     r3 |= (row == 3u) ? v : 0u;
 }
 
-// Replay-mode spawn position: first entry of the permutation row `perm` (16 bytes, a permutation of
-// 0..15) whose cell is empty -- the table walk of _spawn2 (game_numba.py:198-204) done as a 16-lane
-// byte gather: PRMT looks every entry up in the 16-byte "empty" table (z0..z3, 0x80 = empty).
-// Returns the cell index, or 16 when the board is full.
-__device__ __forceinline__ uint32_t first_empty_in_order(uint4 perm, uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3)
+// Replay-mode spawn position.  The reference walks row `p` of randperm and takes the first entry whose
+// cell is empty (_spawn2, game_numba.py:198-204).  Equivalently: among the empty cells take the one with
+// the smallest RANK in that row.  `keys` is the row in inverse form, keys[c] = 16*rank(c) + c (see
+// ml2048_pack_randperm_keys); one min-reduction over the sixteen keys (as 16-bit lanes, DPX three-input
+// min), with occupied cells pushed out of range, yields the winner.  Returns the cell, or 16 if the board is full.
+ML2048_FN uint32_t first_empty_by_rank(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t n0, uint32_t n1,
+                                       uint32_t n2, uint32_t n3)
 {
-    uint32_t hit[4];
-    const uint32_t pw[4] = {perm.x, perm.y, perm.z, perm.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t p = pw[i];
-        uint32_t s = p & 0x07070707u;
-        s |= s >> 4;                                 // byte0 = p0|p1<<4, byte2 = p2|p3<<4
-        const uint32_t sel = prmt(s, 0u, 0x4420);    // selector nibbles (p0,p1,p2,p3) mod 8
-        const uint32_t lo = prmt(z0, z1, sel);       // cells 0..7
-        const uint32_t hi = prmt(z2, z3, sel);       // cells 8..15
-        const uint32_t up = prmt_sign(p << 4, 0u, 0xba98);  // 0xff where p >= 8
-        hit[i] = (lo & ~up) | (hi & up);
-    }
-    uint32_t h = hit[0], p = pw[0];
-    if (h == 0u) { h = hit[1]; p = pw[1]; }
-    if (h == 0u) { h = hit[2]; p = pw[2]; }
-    if (h == 0u) { h = hit[3]; p = pw[3]; }
-    if (h == 0u) return 16u;
-    const uint32_t sh = (uint32_t)(__ffs((int)h) - 1) & ~7u;
-    return (p >> sh) & 0xffu;
+    // widen every key byte to a 16-bit lane whose HIGH byte is 0xff when the cell is occupied, so any
+    // occupied lane (>= 0xff00) loses against any empty one (<= 0x00ff)
+    const uint32_t o0 = prmt_sign(n0, 0u, 0xba98), o1 = prmt_sign(n1, 0u, 0xba98);
+    const uint32_t o2 = prmt_sign(n2, 0u, 0xba98), o3 = prmt_sign(n3, 0u, 0xba98);
+    const uint32_t a0 = prmt(k0, o0, 0x5140), a1 = prmt(k0, o0, 0x7362);
+    const uint32_t b0 = prmt(k1, o1, 0x5140), b1 = prmt(k1, o1, 0x7362);
+    const uint32_t c0 = prmt(k2, o2, 0x5140), c1 = prmt(k2, o2, 0x7362);
+    const uint32_t d0 = prmt(k3, o3, 0x5140), d1 = prmt(k3, o3, 0x7362);
+    uint32_t m = min3_u16x2(min3_u16x2(a0, a1, b0), min3_u16x2(b1, c0, c1), min3_u16x2(d0, d1, d1));
+    m = (m & 0xffffu) < (m >> 16) ? (m & 0xffffu) : (m >> 16);
+    return m >= 0xff00u ? 16u : (m & 15u);
 }
 
-// 16-bit mask of empty cells from the per-row 0x80 flags (multiply gathers bits 7,15,23,31 into a nibble)
-__device__ __forceinline__ uint32_t empties16(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3)
+// 16-bit mask of empty cells from the per-row 0x80 "empty" flags (multiply gathers bits 7,15,23,31 into a nibble)
+ML2048_FN uint32_t empties16(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3)
 {
     const uint32_t m = 0x00204081u;
     return ((z0 * m) >> 28) | (((z1 * m) >> 24) & 0xf0u) | (((z2 * m) >> 20) & 0xf00u) | (((z3 * m) >> 16) & 0xf000u);
 }
 
 // index of the k-th (0-based) set bit of a 16-bit mask; k < popc(mask)
-__device__ __forceinline__ uint32_t kth_set_bit16(uint32_t mask, uint32_t k)
+ML2048_FN uint32_t kth_set_bit16(uint32_t mask, uint32_t k)
 {
     uint32_t pos = 0u, c;
-    c = __popc(mask & 0xffu);
+    c = popc32(mask & 0xffu);
     if (k >= c) { k -= c; pos = 8u; mask >>= 8; }
-    c = __popc(mask & 0xfu);
+    c = popc32(mask & 0xfu);
     if (k >= c) { k -= c; pos += 4u; mask >>= 4; }
-    c = __popc(mask & 0x3u);
+    c = popc32(mask & 0x3u);
     if (k >= c) { k -= c; pos += 2u; mask >>= 2; }
     c = mask & 1u;
     if (k >= c) { pos += 1u; }
     return pos;
 }
 
-// max tile exponent of a board
-__device__ __forceinline__ uint32_t max_cell(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+// max tile exponent of a board (byte-wise max by compare-and-select; cells <= 0x7f)
+ML2048_FN uint32_t max_bytes(uint32_t a, uint32_t b)
 {
-    uint32_t m = __vmaxu4(__vmaxu4(r0, r1), __vmaxu4(r2, r3));
-    m = __vmaxu4(m, m >> 16);
-    m = __vmaxu4(m, m >> 8);
+    // 0xff where a >= b: (a | 0x80) - b keeps bit 7 set exactly when no borrow
+    const uint32_t ge = prmt_sign(((a | kHi) - b), 0u, 0xba98);
+    return (a & ge) | (b & ~ge);
+}
+
+ML2048_FN uint32_t max_cell(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+{
+    uint32_t m = max_bytes(max_bytes(r0, r1), max_bytes(r2, r3));
+    m = max_bytes(m, m >> 16);
+    m = max_bytes(m, m >> 8);
     return m & 0xffu;
 }
 
 // Philox4x32-10 (Salmon et al., SC'11), counter-based: out = f(counter, key)
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+struct u32x4 {
+    uint32_t x, y, z, w;
+};
+
+ML2048_FN u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += W0;
-        key.y += W1;
+        const uint32_t hi0 = umulhi32(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = umulhi32(M1, c2), lo1 = M1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += W0;
+        k1 += W1;
     }
-    return ctr;
+    return u32x4{c0, c1, c2, c3};
 }
 
 }  // namespace ml2048

@@ -143,62 +143,61 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_ar
     if (live) {
         const uint4 bd = reinterpret_cast<const uint4 *>(a.board_in)[g];
         const uint64_t slot = (uint64_t)(a.slot_base + g);
-        uint4 rnd = make_uint4(0, 0, 0, 0);
+        u32x4 rnd = {0u, 0u, 0u, 0u};
         if (kRng == ML2048_RNG_PHILOX || a.action_mode == ML2048_ACTIONS_RANDOM_VALID)
-            rnd = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)a.philox_counter,
-                                           (uint32_t)(a.philox_counter >> 32)),
-                                make_uint2((uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32)));
+            rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)a.philox_counter,
+                                (uint32_t)(a.philox_counter >> 32), (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
         uint32_t action;
         if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
             // uniform over the valid directions (policy/random.py:17-27); 0 when the game is over
             const uint32_t vm = reinterpret_cast<const uint32_t *>(a.valid_in)[g];
             const uint32_t bits = (vm & 1u) | ((vm >> 7) & 2u) | ((vm >> 14) & 4u) | ((vm >> 21) & 8u);
-            const uint32_t nv = __popc(bits);
-            action = nv ? kth_set_bit16(bits, __umulhi(rnd.z, nv)) : 0u;
+            const uint32_t nv = popc32(bits);
+            action = nv ? kth_set_bit16(bits, umulhi32(rnd.z, nv)) : 0u;
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
         } else {
             action = load_action(a.actions, a.action_dtype, g);
         }
 
         uint32_t r0 = bd.x, r1 = bd.y, r2 = bd.z, r3 = bd.w;
-        Fusions f = {0u, 0u, 0u, 0ull};
-        move_board<kLog>(r0, r1, r2, r3, action & 3u, f);
+        Fusions f;
+        move_board(r0, r1, r2, r3, action & 3u, f);
         // valid_actions[action] (game_numba.py:718) == "the move changes the board"; out-of-range
         // actions (which the reference would index out of bounds with) count as invalid moves
         const bool moved = (action < 4u) && (((r0 ^ bd.x) | (r1 ^ bd.y) | (r2 ^ bd.z) | (r3 ^ bd.w)) != 0u);
 
         if (moved) {
             // reward_fn (:728) and the score increment (:729-731)
+            const uint32_t gain = fusion_gain(f);
             float reward;
             if (a.reward_kind == ML2048_REWARD_IMPROVED) {
                 // potential shaping on cell 0, game_numba.py:455-466 (all terms are exact integers in f32)
                 const uint32_t s0 = r0 & 0xffu, p0 = bd.x & 0xffu;
                 const int extra = (s0 ? (64 << s0) : 0) - (p0 ? (64 << p0) : 0);
-                reward = (float)((int)f.gain + extra);
+                reward = (float)((int)gain + extra);
             } else if (a.reward_kind == ML2048_REWARD_RANK) {
-                reward = (float)f.rank;
+                reward = (float)fusion_rank(f);
             } else if (a.reward_kind == ML2048_REWARD_MAXCELL) {
                 const uint32_t cur = max_cell(r0, r1, r2, r3), old = max_cell(bd.x, bd.y, bd.z, bd.w);
                 reward = (float)f.count + ((cur > old) ? (float)(1u << cur) : 0.0f);
             } else {
-                reward = (float)f.gain;
+                reward = (float)gain;
             }
-            const float score = a.score[g] + (float)f.gain;
+            const float score = a.score[g] + (float)gain;
             const int32_t nstep = a.step[g] + 1;
 
             // spawn one tile (_spawn2 with count = 1, game_numba.py:733)
-            const uint32_t z0 = occupied_flags(r0) ^ kHi, z1 = occupied_flags(r1) ^ kHi;
-            const uint32_t z2 = occupied_flags(r2) ^ kHi, z3 = occupied_flags(r3) ^ kHi;
+            const uint32_t n0 = occupied_flags(r0), n1 = occupied_flags(r1), n2 = occupied_flags(r2), n3 = occupied_flags(r3);
             uint32_t cell, value;
             if (kRng == ML2048_RNG_REPLAY) {
                 const uint32_t row = (uint32_t)((uint64_t)(a.rand_seed + (int64_t)slot) % (uint64_t)kRandRows);
-                const uint4 perm = __ldg(reinterpret_cast<const uint4 *>(a.randperm) + row);
-                cell = first_empty_in_order(perm, z0, z1, z2, z3);
+                const uint4 keys = __ldg(reinterpret_cast<const uint4 *>(a.randperm_keys) + row);
+                cell = first_empty_by_rank(keys.x, keys.y, keys.z, keys.w, n0, n1, n2, n3);
                 value = 2u - ((a.two_mask >> (cell & 15u)) & 1u);
             } else {
-                const uint32_t empties = empties16(z0, z1, z2, z3);
-                const uint32_t ne = __popc(empties);
-                cell = ne ? kth_set_bit16(empties, __umulhi(rnd.x, ne)) : 16u;
+                const uint32_t empties = empties16(n0 ^ kHi, n1 ^ kHi, n2 ^ kHi, n3 ^ kHi);
+                const uint32_t ne = popc32(empties);
+                cell = ne ? kth_set_bit16(empties, umulhi32(rnd.x, ne)) : 16u;
                 value = (rnd.y < a.two_threshold) ? 1u : 2u;
             }
             if (cell < 16u) put_cell(r0, r1, r2, r3, cell, value);
@@ -212,13 +211,8 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_ar
             a.terminated[g] = dead ? 1 : 0;
             a.invalid[g] = 0;
             if (kLog) {
-                // expand the sixteen 4-bit counters to the reference's u8[16] `merged`
-                const uint32_t lo = (uint32_t)f.log, hi = (uint32_t)(f.log >> 32);
-                uint32_t m0 = lo & 0xffffu, m1 = lo >> 16, m2 = hi & 0xffffu, m3 = hi >> 16;
-                m0 = (m0 | (m0 << 8)) & 0x00ff00ffu; m0 = (m0 | (m0 << 4)) & 0x0f0f0f0fu;
-                m1 = (m1 | (m1 << 8)) & 0x00ff00ffu; m1 = (m1 | (m1 << 4)) & 0x0f0f0f0fu;
-                m2 = (m2 | (m2 << 8)) & 0x00ff00ffu; m2 = (m2 | (m2 << 4)) & 0x0f0f0f0fu;
-                m3 = (m3 | (m3 << 8)) & 0x00ff00ffu; m3 = (m3 | (m3 << 4)) & 0x0f0f0f0fu;
+                uint32_t m0, m1, m2, m3;
+                fusion_log(f, m0, m1, m2, m3);
                 reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(m0, m1, m2, m3);
             }
             if (dead && a.stats) {
@@ -361,11 +355,11 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
             v0 = 2u - ((a.two_mask >> (c0 & 15u)) & 1u);
             v1 = 2u - ((a.two_mask >> (c1 & 15u)) & 1u);
         } else {
-            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)a.philox_counter,
-                                                       (uint32_t)(a.philox_counter >> 32) ^ 0x80000000u),
-                                            make_uint2((uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32)));
+            const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)a.philox_counter,
+                                            (uint32_t)(a.philox_counter >> 32) ^ 0x80000000u, (uint32_t)a.philox_seed,
+                                            (uint32_t)(a.philox_seed >> 32));
             c0 = rnd.x >> 28;
-            c1 = __umulhi(rnd.y, 15u);
+            c1 = umulhi32(rnd.y, 15u);
             c1 += (c1 >= c0) ? 1u : 0u;
             v0 = (rnd.z < a.two_threshold) ? 1u : 2u;
             v1 = (rnd.w < a.two_threshold) ? 1u : 2u;
@@ -434,12 +428,12 @@ __global__ void __launch_bounds__(kStepThreads) sample_random_valid_kernel(const
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= num_games) return;
     const uint64_t slot = (uint64_t)(slot_base + g);
-    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)),
-                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)counter, (uint32_t)(counter >> 32),
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
     const uint32_t vm = valid[g];
     const uint32_t bits = (vm & 1u) | ((vm >> 7) & 2u) | ((vm >> 14) & 4u) | ((vm >> 21) & 8u);
-    const uint32_t nv = __popc(bits);
-    actions[g] = (uint8_t)(nv ? kth_set_bit16(bits, __umulhi(rnd.z, nv)) : 0u);
+    const uint32_t nv = popc32(bits);
+    actions[g] = (uint8_t)(nv ? kth_set_bit16(bits, umulhi32(rnd.z, nv)) : 0u);
 }
 
 __global__ void fill_terminated_kernel(uint8_t *terminated, int64_t num_games, int64_t padded)
@@ -497,7 +491,7 @@ int ml2048_step(const ml2048_step_args *args, void *stream)
         return ML2048_E_NULL;
     if (a.board_in == a.board_out) return ML2048_E_NULL;
     if (misaligned(a.board_in, 16) || misaligned(a.board_out, 16) || misaligned(a.valid_out, 4) || misaligned(a.merged, 16) ||
-        misaligned(a.onehot_out, 16) || misaligned(a.valid_in, 4) || misaligned(a.randperm, 16) || misaligned(a.stats, 8))
+        misaligned(a.onehot_out, 16) || misaligned(a.valid_in, 4) || misaligned(a.stats, 8))
         return ML2048_E_ALIGN;
     if (a.reward_kind < 0 || a.reward_kind > ML2048_REWARD_MAXCELL) return ML2048_E_ENUM;
     if (a.action_mode == ML2048_ACTIONS_GIVEN) {
@@ -513,7 +507,8 @@ int ml2048_step(const ml2048_step_args *args, void *stream)
     if (a.onehot_out && (a.onehot_dtype < ML2048_ONEHOT_F32 || a.onehot_dtype > ML2048_ONEHOT_U8)) return ML2048_E_ENUM;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a.rng_mode == ML2048_RNG_REPLAY) {
-        if (!a.randperm) return ML2048_E_NULL;
+        if (!a.randperm_keys) return ML2048_E_NULL;
+        if (misaligned(a.randperm_keys, 16)) return ML2048_E_ALIGN;
         return a.merged ? launch_step_onehot<ML2048_RNG_REPLAY, true>(a, s) : launch_step_onehot<ML2048_RNG_REPLAY, false>(a, s);
     }
     if (a.rng_mode == ML2048_RNG_PHILOX)
@@ -663,6 +658,26 @@ uint32_t ml2048_two_mask(const float *host_randfloat16, double two_prob)
     for (int c = 0; c < 16; ++c)
         if ((double)host_randfloat16[c] < two_prob) m |= 1u << c;
     return m;
+}
+
+int ml2048_pack_randperm_keys(const uint8_t *host_randperm, uint8_t *host_keys, int64_t rows)
+{
+    // inverse form of each permutation row: keys[row][cell] = 16 * rank(cell) + cell, where rank(cell) is the
+    // position of `cell` in the row, i.e. the order in which _spawn2 (game_numba.py:198-204) visits it
+    if (!host_randperm || !host_keys) return ML2048_E_NULL;
+    if (rows <= 0) return ML2048_E_SIZE;
+    for (int64_t r = 0; r < rows; ++r) {
+        const uint8_t *p = host_randperm + 16 * r;
+        uint8_t *k = host_keys + 16 * r;
+        unsigned seen = 0;
+        for (int i = 0; i < 16; ++i) {
+            if (p[i] > 15) return ML2048_E_ENUM;
+            seen |= 1u << p[i];
+            k[p[i]] = (uint8_t)(16 * i + p[i]);
+        }
+        if (seen != 0xffffu) return ML2048_E_ENUM;  // not a permutation of 0..15
+    }
+    return 0;
 }
 
 uint32_t ml2048_two_threshold(double two_prob)

@@ -213,7 +213,10 @@ class VecGame:
             self._onehot = torch.zeros((m, 16, 16), dtype=onehot_dtype, device=dev) if onehot_dtype is not None else None
             self._actions_dev = torch.zeros((m,), dtype=torch.int64, device=dev)  # staging for host actions
             self._actions_out = torch.zeros((m,), dtype=torch.uint8, device=dev)
-            self._randperm_dev = torch.zeros((RAND_ROWS, 16), dtype=torch.uint8, device=dev)
+            # row 0: the reference's randperm table, row 1: the same table in inverse ("rank key") form
+            self._tables_dev = torch.zeros((2, RAND_ROWS, 16), dtype=torch.uint8, device=dev)
+            self._randperm_dev = self._tables_dev[0]
+            self._randkeys_dev = self._tables_dev[1]
             self._game_count_dev = torch.zeros((1,), dtype=torch.int64, device=dev)  # survives reset(), :582
             self._reset_count_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
             self._reset_indices_dev = torch.zeros((m,), dtype=torch.int64, device=dev)
@@ -227,6 +230,7 @@ class VecGame:
         # host copies of the random tables, as in the reference (game_numba.py:577-580)
         self._randperm = np.empty((RAND_ROWS, 16), dtype=np.uint8)
         self._randfloat = np.empty((RAND_ROWS,), dtype=np.float32)
+        self._tables_host = np.zeros((2, RAND_ROWS, 16), dtype=np.uint8)  # staging: randperm + its inverse-form keys
         self._rand_step = 0
         self._two_mask = 0
         self._two_threshold = int(self._lib.ml2048_two_threshold(self._two_prob))
@@ -268,7 +272,7 @@ class VecGame:
         a.invalid = self._p(self._invalid)
         a.merged = self._p(self._merged)
         a.onehot_out = self._p(self._onehot)
-        a.randperm = self._p(self._randperm_dev)
+        a.randperm_keys = self._p(self._randkeys_dev)
         a.two_threshold = self._two_threshold
         a.stats = self._p(self._stats_dev)
         p = self._prep_args
@@ -330,7 +334,10 @@ class VecGame:
     def _upload_tables(self) -> None:
         """Tables changed on the host: ship the permutations (16 KiB) and fold the 2-vs-4 uniforms into
         a 16-bit mask (only randfloat[0:16] is ever read, indexed by CELL: game_numba.py:207)."""
-        self._randperm_dev.copy_(torch.from_numpy(self._randperm))
+        _lib.check(self._lib.ml2048_pack_randperm_keys(self._randperm.ctypes.data, self._tables_host[1].ctypes.data, RAND_ROWS),
+                   "ml2048_pack_randperm_keys")
+        self._tables_host[0] = self._randperm
+        self._tables_dev.copy_(torch.from_numpy(self._tables_host))
         self._two_mask = int(self._lib.ml2048_two_mask(self._randfloat.ctypes.data, self._two_prob))
 
     # ------------------------------------------------------------------------------------------
@@ -516,7 +523,7 @@ class VecGame:
         tensors = {
             name: getattr(self, name).clone()
             for name in ("_board", "_valid", "_id", "_step", "_score", "_reward", "_terminated_padded", "_invalid",
-                         "_randperm_dev", "_game_count_dev", "_stats_dev")
+                         "_tables_dev", "_game_count_dev", "_stats_dev")
         }
         if self._merged is not None:
             tensors["_merged"] = self._merged.clone()

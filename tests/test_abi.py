@@ -141,3 +141,18 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"(import\s+oracle|from\s+oracle|from\s+\.+oracle|liboracle|oracle/)", text), f"{f} reaches into oracle/"
     code = "import sys; import ml2048_b200, ml2048_b200.vecgame, ml2048_b200.sharding; assert not any(m.startswith('oracle') for m in sys.modules)"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_pack_randperm_keys(lib):
+    rng = np.random.default_rng(0)
+    perm = np.argsort(rng.random((1024, 16)), axis=1).astype(np.uint8)
+    keys = np.zeros_like(perm)
+    assert lib.ml2048_pack_randperm_keys(perm.ctypes.data, keys.ctypes.data, 1024) == 0
+    want = np.empty_like(perm)
+    want[np.arange(1024)[:, None], perm] = (np.arange(16, dtype=np.uint8) * 16)[None, :] + perm
+    np.testing.assert_array_equal(keys, want)
+    assert (keys & 15 == np.arange(16)).all()
+    bad = perm.copy()
+    bad[3, 0] = bad[3, 1]
+    assert lib.ml2048_pack_randperm_keys(bad.ctypes.data, keys.ctypes.data, 1024) == -4
+    assert lib.ml2048_pack_randperm_keys(None, keys.ctypes.data, 1024) == -1

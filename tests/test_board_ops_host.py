@@ -1,0 +1,169 @@
+"""
+The product's device arithmetic (ml2048_b200/csrc/board_ops.cuh) compiled as plain C++ (tests/host_shim)
+and checked against the CPU oracle / golden fixtures WITHOUT a GPU: every 4-cell line in every board
+position and direction (18^4 x 4 x 4), the reference-generated board set, random boards for the mask,
+the replay spawn position, and Philox against its published known-answer vectors.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import golden
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SHIM_SRC = os.path.join(HERE, "host_shim", "board_ops_host.cpp")
+SHIM_LIB = os.path.join(HERE, "host_shim", "libboard_ops_host.so")
+HEADER = os.path.join(os.path.dirname(HERE), "ml2048_b200", "csrc", "board_ops.cuh")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    if not os.path.exists(SHIM_LIB) or os.path.getmtime(SHIM_LIB) < max(os.path.getmtime(SHIM_SRC), os.path.getmtime(HEADER)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", SHIM_LIB, SHIM_SRC],
+                       check=True)
+    lib = ctypes.CDLL(SHIM_LIB)
+    vp, i64, u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32
+    lib.hs_move_batch.argtypes = [vp, i64, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    lib.hs_first_empty_batch.argtypes = [vp, vp, i64, vp]
+    lib.hs_valid_mask.argtypes = [vp]
+    lib.hs_valid_mask.restype = u32
+    lib.hs_max_cell.argtypes = [vp]
+    lib.hs_max_cell.restype = u32
+    lib.hs_empties16.argtypes = [vp]
+    lib.hs_empties16.restype = u32
+    lib.hs_kth_set_bit16.argtypes = [u32, u32]
+    lib.hs_kth_set_bit16.restype = u32
+    lib.hs_philox.argtypes = [vp, vp, vp]
+    return lib
+
+
+def _move_batch(shim, boards, action):
+    n = boards.shape[0]
+    b = np.ascontiguousarray(boards, np.uint8)
+    out = np.empty_like(b)
+    gain = np.empty(n, np.uint32)
+    rank = np.empty(n, np.uint32)
+    count = np.empty(n, np.uint32)
+    merged = np.empty((n, 16), np.uint8)
+    mask = np.empty(n, np.uint32)
+    shim.hs_move_batch(b.ctypes.data, n, action, out.ctypes.data, gain.ctypes.data, rank.ctypes.data, count.ctypes.data,
+                       merged.ctypes.data, mask.ctypes.data)
+    return out, gain, rank, count, merged, mask.view(np.uint8).reshape(n, 4)
+
+
+def test_every_line_every_position_every_direction(shim):
+    """All 18^4 lines, as each of the 4 rows (left/right) and each of the 4 columns (up/down), with noise
+    in the other cells, against the reference's own _push_row table (tests/golden/line_table.npz)."""
+    tab = golden("line_table.npz")
+    v = np.arange(18, dtype=np.uint8)
+    lines = np.stack(np.meshgrid(v, v, v, v, indexing="ij"), axis=-1).reshape(-1, 4)
+    n = lines.shape[0]
+    rng = np.random.default_rng(1)
+    weights = (2 << np.arange(18)).astype(np.int64)
+    for action, name in ((0, "first"), (1, "last"), (2, "first"), (3, "last")):
+        pushed, fused = tab[f"pushed_{name}"], tab[f"fused_{name}"]
+        want_gain = np.where(fused > 0, weights[fused], 0).sum(axis=1)
+        for pos in range(4):
+            boards = rng.integers(0, 18, size=(n, 16)).astype(np.uint8).reshape(n, 4, 4)
+            if action < 2:
+                boards[:, pos, :] = lines
+            else:
+                boards[:, :, pos] = lines
+            out, gain, rank, count, merged, _ = _move_batch(shim, boards.reshape(n, 16), action)
+            out = out.reshape(n, 4, 4)
+            got = out[:, pos, :] if action < 2 else out[:, :, pos]
+            bad = np.flatnonzero((got != pushed).any(axis=1))
+            assert bad.size == 0, (action, pos, lines[bad[0]], got[bad[0]], pushed[bad[0]])
+        # rewards / merged on boards where only this line can fuse (other lines all distinct, no zeros needed)
+        filler = np.array([[1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12], [13, 14, 15, 16]], np.uint8)
+        boards = np.broadcast_to(filler if action < 2 else filler.T, (n, 4, 4)).copy()
+        if action < 2:
+            boards[:, 0, :] = lines
+        else:
+            boards[:, :, 0] = lines
+        out, gain, rank, count, merged, _ = _move_batch(shim, boards.reshape(n, 16), action)
+        np.testing.assert_array_equal(gain.astype(np.int64), want_gain)
+        np.testing.assert_array_equal(count, (fused > 0).sum(axis=1))
+        np.testing.assert_array_equal(rank, np.where(fused > 0, fused.astype(np.int64) + 1, 0).sum(axis=1))
+        want_merged = np.zeros((n, 18), np.uint8)
+        for j in range(2):
+            np.add.at(want_merged, (np.arange(n), fused[:, j]), (fused[:, j] > 0).astype(np.uint8))
+        np.testing.assert_array_equal(merged, want_merged[:, :16])
+
+
+def test_reference_board_set(shim, oracle):
+    g = golden("boards.npz")
+    boards = g["boards"]
+    names = [str(x) for x in g["reward_names"]]
+    for action in range(4):
+        out, gain, rank, count, merged, mask = _move_batch(shim, boards, action)
+        np.testing.assert_array_equal(out, g["moved"][:, action])
+        np.testing.assert_array_equal(merged, g["merged"][:, action])
+        np.testing.assert_array_equal(mask, g["mask"])
+        np.testing.assert_array_equal(gain.astype(np.float64), g["rewards"][:, action, names.index("normal")])
+        np.testing.assert_array_equal(rank.astype(np.float64), g["rewards"][:, action, names.index("rank")])
+        # "the move changes the board" == valid_actions[action] (game_numba.py:718)
+        np.testing.assert_array_equal((out != boards).any(axis=1), g["mask"][:, action] != 0)
+
+
+def test_mask_and_max_on_random_boards(shim, oracle):
+    rng = np.random.default_rng(5)
+    n = 20000
+    dens = rng.choice([0.1, 0.5, 0.9, 1.0], size=n)
+    hi = rng.choice([2, 3, 5, 17], size=n)
+    boards = (rng.integers(0, 1 << 30, size=(n, 16)) % hi[:, None] + 1).astype(np.uint8)
+    boards[rng.random((n, 16)) >= dens[:, None]] = 0
+    for i in range(n):
+        got = shim.hs_valid_mask(boards[i].ctypes.data)
+        want = int(oracle.board_valid(boards[i]).view(np.uint32)[0])
+        assert got == want, (boards[i], hex(got), hex(want))
+        assert shim.hs_max_cell(boards[i].ctypes.data) == boards[i].max()
+        e = shim.hs_empties16(boards[i].ctypes.data)
+        assert e == sum(1 << c for c in range(16) if boards[i][c] == 0)
+
+
+def test_spawn_position_matches_table_walk(shim):
+    """first_empty_by_rank on the inverse-form keys == the reference's walk over the permutation row."""
+    rng = np.random.default_rng(9)
+    n = 50000
+    perms = np.argsort(rng.random((n, 16)), axis=1).astype(np.uint8)
+    keys = np.empty((n, 16), np.uint8)
+    keys[np.arange(n)[:, None], perms] = (np.arange(16, dtype=np.uint8) * 16)[None, :] + perms
+    boards = rng.integers(1, 5, size=(n, 16)).astype(np.uint8)
+    boards[rng.random((n, 16)) < rng.random((n, 1))] = 0
+    boards[:50] = 1  # full boards
+    boards[50:100] = 1
+    boards[50:100, 15] = 0  # only cell 15 empty (its key can be 0xff)
+    cells = np.empty(n, np.uint32)
+    shim.hs_first_empty_batch(keys.ctypes.data, boards.ctypes.data, n, cells.ctypes.data)
+    empty_in_order = np.take_along_axis(boards, perms.astype(np.int64), axis=1) == 0
+    want = np.where(empty_in_order.any(axis=1), perms[np.arange(n), empty_in_order.argmax(axis=1)], 16)
+    np.testing.assert_array_equal(cells, want)
+
+
+def test_kth_set_bit(shim):
+    for mask in list(range(1, 1 << 12, 37)) + [0xFFFF, 0x8000, 0x0001, 0xF0F0]:
+        bits = [i for i in range(16) if mask >> i & 1]
+        for k, want in enumerate(bits):
+            assert shim.hs_kth_set_bit16(mask, k) == want
+
+
+def test_philox_known_answers(shim):
+    # Random123 kat_vectors: philox4x32-10
+    cases = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in cases:
+        c = np.array(ctr, np.uint32)
+        k = np.array(key, np.uint32)
+        out = np.zeros(4, np.uint32)
+        shim.hs_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+        assert tuple(int(x) for x in out) == want
