@@ -43,7 +43,7 @@ def test_struct_layouts_match_header(lib, tmp_path):
     src.write_text(
         f'#include "{HEADER}"\n#include <stdio.h>\n#include <stddef.h>\n'
         "int main(void){printf(\"%zu %zu %zu %zu %zu %zu\\n\", sizeof(ml2048_step_args), sizeof(ml2048_prepare_args),"
-        " sizeof(ml2048_stats), offsetof(ml2048_step_args, randperm), offsetof(ml2048_step_args, stats),"
+        " sizeof(ml2048_stats), offsetof(ml2048_step_args, randperm_keys), offsetof(ml2048_step_args, stats),"
         " offsetof(ml2048_prepare_args, scratch));return 0;}\n"
     )
     exe = tmp_path / "sz"
@@ -53,7 +53,7 @@ def test_struct_layouts_match_header(lib, tmp_path):
         ctypes.sizeof(_lib.StepArgs),
         ctypes.sizeof(_lib.PrepareArgs),
         _lib.STATS_WORDS * 8,
-        _lib.StepArgs.randperm.offset,
+        _lib.StepArgs.randperm_keys.offset,
         _lib.StepArgs.stats.offset,
         _lib.PrepareArgs.scratch.offset,
     ]
