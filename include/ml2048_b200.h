@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ML2048_ABI_VERSION 2
+#define ML2048_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define ML2048_API __attribute__((visibility("default")))
@@ -76,6 +76,20 @@ typedef struct {
 
 #define ML2048_STATS_REPLICAS 64
 
+/* One pre-drawn runner step of the host random schedule, kept on the device so that a CUDA graph can replay
+ * many steps without host work.  The reference draws these numbers on the host in every prepare()/step()
+ * (game_numba.py:622-626, :670); none depends on game state, so they can be drawn ahead (ml2048_b200/vecgame.py
+ * draws them from the same generator in the same order).  When `sched` is set in the argument structs the
+ * kernels read entry sched[*sched_cursor] INSTEAD of the scalar fields rand_base / rand_seed / two_mask /
+ * philox_counter, and the random tables of slot `table` of the table ring. */
+typedef struct {
+    int64_t rand_base;        /* prepare: _rand_step + rand_offset (:651) */
+    int64_t rand_seed;        /* step:    _rand_step + rand_offset (:681) */
+    uint64_t philox_counter;  /* prepare uses this value, step uses this value + 1 */
+    uint32_t two_mask;        /* 2-vs-4 mask of the tables in force */
+    uint32_t table;           /* slot of the table ring holding the tables in force */
+} ml2048_sched_entry;
+
 /* Arguments of one environment step.  Replaces VecGame.step + _vec_step
  * (game_numba.py:660-698, 701-738) including the prev_state / prev_valid_actions copies (:672-673):
  * boards and masks are ping-pong buffers, so board_in / valid_in ARE the "prev" arrays afterwards. */
@@ -117,6 +131,12 @@ typedef struct {
     uint64_t philox_counter; /* caller increments once per step */
 
     ml2048_stats *stats;     /* [ML2048_STATS_REPLICAS] or null: finished-episode statistics */
+
+    /* device-resident schedule (or null: use the scalar fields above) */
+    const ml2048_sched_entry *sched;
+    const int64_t *sched_cursor;   /* device scalar: index of the entry to use */
+    int64_t *sched_cursor_next;    /* device scalar (not aliasing sched_cursor) or null: receives *sched_cursor + 1 */
+    int64_t table_stride;          /* bytes between consecutive slots of the table ring (randperm_keys = slot 0) */
 } ml2048_step_args;
 
 /* Arguments of the auto-reset.  Replaces the host loop of VecGame.prepare (game_numba.py:629-658):
@@ -154,6 +174,11 @@ typedef struct {
     int64_t *reset_count;  /* device scalar out: number of slots reset by this call */
     int64_t *reset_indices;/* [num_games] out, ascending slots (np.flatnonzero, :629), or null */
     int32_t *scratch;      /* [ml2048_prepare_scratch_ints(num_games)] */
+
+    /* device-resident schedule (or null), see ml2048_sched_entry; prepare never advances the cursor */
+    const ml2048_sched_entry *sched;
+    const int64_t *sched_cursor;
+    int64_t table_stride;  /* bytes between consecutive slots of the table ring (randperm = slot 0) */
 } ml2048_prepare_args;
 
 /* ---- entry points ---------------------------------------------------------------------------- */

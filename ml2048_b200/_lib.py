@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libml2048_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 STATS_REPLICAS = 64
 STATS_WORDS = 24  # 20 histogram bins + episodes, score_sum, step_sum, score_max (unsigned long long each)
 
@@ -57,6 +57,10 @@ class StepArgs(C.Structure):
         ("philox_seed", C.c_uint64),
         ("philox_counter", C.c_uint64),
         ("stats", C.c_void_p),
+        ("sched", C.c_void_p),
+        ("sched_cursor", C.c_void_p),
+        ("sched_cursor_next", C.c_void_p),
+        ("table_stride", C.c_int64),
     ]
 
 
@@ -91,6 +95,9 @@ class PrepareArgs(C.Structure):
         ("reset_count", C.c_void_p),
         ("reset_indices", C.c_void_p),
         ("scratch", C.c_void_p),
+        ("sched", C.c_void_p),
+        ("sched_cursor", C.c_void_p),
+        ("table_stride", C.c_int64),
     ]
 
 

@@ -140,13 +140,28 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_ar
     const bool live = g < a.num_games;
     uint4 out_board = make_uint4(0, 0, 0, 0);
 
+    // per-step random schedule: scalar arguments, or the pre-drawn entry a CUDA graph replays
+    int64_t rand_seed = a.rand_seed;
+    uint32_t two_mask = a.two_mask;
+    uint64_t philox_counter = a.philox_counter;
+    const uint8_t *keys_table = a.randperm_keys;
+    if (a.sched) {
+        const int64_t cursor = *a.sched_cursor;
+        const ml2048_sched_entry e = a.sched[cursor];
+        rand_seed = e.rand_seed;
+        two_mask = e.two_mask;
+        philox_counter = e.philox_counter + 1ull;
+        keys_table += (int64_t)e.table * a.table_stride;
+        if (a.sched_cursor_next && blockIdx.x == 0 && threadIdx.x == 0) *a.sched_cursor_next = cursor + 1;
+    }
+
     if (live) {
         const uint4 bd = reinterpret_cast<const uint4 *>(a.board_in)[g];
         const uint64_t slot = (uint64_t)(a.slot_base + g);
         u32x4 rnd = {0u, 0u, 0u, 0u};
         if (kRng == ML2048_RNG_PHILOX || a.action_mode == ML2048_ACTIONS_RANDOM_VALID)
-            rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)a.philox_counter,
-                                (uint32_t)(a.philox_counter >> 32), (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
+            rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)philox_counter,
+                                (uint32_t)(philox_counter >> 32), (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
         uint32_t action;
         if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
             // uniform over the valid directions (policy/random.py:17-27); 0 when the game is over
@@ -190,10 +205,10 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_ar
             const uint32_t n0 = occupied_flags(r0), n1 = occupied_flags(r1), n2 = occupied_flags(r2), n3 = occupied_flags(r3);
             uint32_t cell, value;
             if (kRng == ML2048_RNG_REPLAY) {
-                const uint32_t row = (uint32_t)((uint64_t)(a.rand_seed + (int64_t)slot) % (uint64_t)kRandRows);
-                const uint4 keys = __ldg(reinterpret_cast<const uint4 *>(a.randperm_keys) + row);
+                const uint32_t row = (uint32_t)((uint64_t)(rand_seed + (int64_t)slot) % (uint64_t)kRandRows);
+                const uint4 keys = __ldg(reinterpret_cast<const uint4 *>(keys_table) + row);
                 cell = first_empty_by_rank(keys.x, keys.y, keys.z, keys.w, n0, n1, n2, n3);
-                value = 2u - ((a.two_mask >> (cell & 15u)) & 1u);
+                value = 2u - ((two_mask >> (cell & 15u)) & 1u);
             } else {
                 const uint32_t empties = empties16(n0 ^ kHi, n1 ^ kHi, n2 ^ kHi, n3 ^ kHi);
                 const uint32_t ne = popc32(empties);
@@ -336,6 +351,17 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += warp_tot[w];
     if (mask == 0u) return;
 
+    int64_t rand_base = a.rand_base;
+    uint32_t two_mask = a.two_mask;
+    uint64_t philox_counter = a.philox_counter;
+    const uint8_t *perm_table = a.randperm;
+    if (a.sched) {
+        const ml2048_sched_entry e = a.sched[*a.sched_cursor];
+        rand_base = e.rand_base;
+        two_mask = e.two_mask;
+        philox_counter = e.philox_counter;
+        perm_table += (int64_t)e.table * a.table_stride;
+    }
     int64_t order = (int64_t)tile_offsets[blockIdx.x] + wbase + inc - mine;  // rank among all reset slots
     const int64_t id_base = *id_base_slot + (a.id_offset ? *a.id_offset : 0);
     uint4 clear16 = reinterpret_cast<const uint4 *>(a.terminated)[i];
@@ -348,15 +374,15 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
         uint32_t c0, c1, v0, v1;
         if (kRng == ML2048_RNG_REPLAY) {
             // the board is empty, so the first two entries of the table row are taken (game_numba.py:648-655)
-            const uint32_t row = (uint32_t)((uint64_t)(a.rand_base + (int64_t)slot) % (uint64_t)kRandRows);
-            const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(a.randperm) + row * 4);
+            const uint32_t row = (uint32_t)((uint64_t)(rand_base + (int64_t)slot) % (uint64_t)kRandRows);
+            const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(perm_table) + row * 4);
             c0 = p & 0xffu;
             c1 = (p >> 8) & 0xffu;
-            v0 = 2u - ((a.two_mask >> (c0 & 15u)) & 1u);
-            v1 = 2u - ((a.two_mask >> (c1 & 15u)) & 1u);
+            v0 = 2u - ((two_mask >> (c0 & 15u)) & 1u);
+            v1 = 2u - ((two_mask >> (c1 & 15u)) & 1u);
         } else {
-            const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)a.philox_counter,
-                                            (uint32_t)(a.philox_counter >> 32) ^ 0x80000000u, (uint32_t)a.philox_seed,
+            const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)philox_counter,
+                                            (uint32_t)(philox_counter >> 32) ^ 0x80000000u, (uint32_t)a.philox_seed,
                                             (uint32_t)(a.philox_seed >> 32));
             c0 = rnd.x >> 28;
             c1 = umulhi32(rnd.y, 15u);
@@ -505,6 +531,11 @@ int ml2048_step(const ml2048_step_args *args, void *stream)
         return ML2048_E_ENUM;
     }
     if (a.onehot_out && (a.onehot_dtype < ML2048_ONEHOT_F32 || a.onehot_dtype > ML2048_ONEHOT_U8)) return ML2048_E_ENUM;
+    if (a.sched) {
+        if (!a.sched_cursor || a.sched_cursor == a.sched_cursor_next) return ML2048_E_NULL;
+        if (misaligned(a.sched, 8) || misaligned(a.sched_cursor, 8) || misaligned(a.sched_cursor_next, 8) || (a.table_stride & 15))
+            return ML2048_E_ALIGN;
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a.rng_mode == ML2048_RNG_REPLAY) {
         if (!a.randperm_keys) return ML2048_E_NULL;
@@ -532,6 +563,10 @@ static int check_prepare_args(const ml2048_prepare_args *args)
     if (a.onehot && (a.onehot_dtype < ML2048_ONEHOT_F32 || a.onehot_dtype > ML2048_ONEHOT_U8)) return ML2048_E_ENUM;
     if (a.rng_mode == ML2048_RNG_REPLAY && !a.randperm) return ML2048_E_NULL;
     if (a.rng_mode != ML2048_RNG_REPLAY && a.rng_mode != ML2048_RNG_PHILOX) return ML2048_E_ENUM;
+    if (a.sched) {
+        if (!a.sched_cursor) return ML2048_E_NULL;
+        if (misaligned(a.sched, 8) || misaligned(a.sched_cursor, 8) || (a.table_stride & 15)) return ML2048_E_ALIGN;
+    }
     return 0;
 }
 

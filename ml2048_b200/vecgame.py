@@ -213,10 +213,13 @@ class VecGame:
             self._onehot = torch.zeros((m, 16, 16), dtype=onehot_dtype, device=dev) if onehot_dtype is not None else None
             self._actions_dev = torch.zeros((m,), dtype=torch.int64, device=dev)  # staging for host actions
             self._actions_out = torch.zeros((m,), dtype=torch.uint8, device=dev)
-            # row 0: the reference's randperm table, row 1: the same table in inverse ("rank key") form
-            self._tables_dev = torch.zeros((2, RAND_ROWS, 16), dtype=torch.uint8, device=dev)
-            self._randperm_dev = self._tables_dev[0]
-            self._randkeys_dev = self._tables_dev[1]
+            # table ring: slot s holds [0] the reference's randperm table and [1] the same table in inverse
+            # ("rank key") form.  Eager calls use one slot; a pre-drawn device schedule uses one slot per refresh.
+            self._table_slots = 1
+            self._tables_dev = torch.zeros((self._table_slots, 2, RAND_ROWS, 16), dtype=torch.uint8, device=dev)
+            self._table_slot = 0
+            self._sched_dev = None                       # int64 (L, 4): ml2048_sched_entry[L]
+            self._sched_cursor_dev = torch.zeros((2,), dtype=torch.int64, device=dev)  # ping-pong like the boards
             self._game_count_dev = torch.zeros((1,), dtype=torch.int64, device=dev)  # survives reset(), :582
             self._reset_count_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
             self._reset_indices_dev = torch.zeros((m,), dtype=torch.int64, device=dev)
@@ -231,6 +234,8 @@ class VecGame:
         self._randperm = np.empty((RAND_ROWS, 16), dtype=np.uint8)
         self._randfloat = np.empty((RAND_ROWS,), dtype=np.float32)
         self._tables_host = np.zeros((2, RAND_ROWS, 16), dtype=np.uint8)  # staging: randperm + its inverse-form keys
+        self._sched_len = 0   # entries of the device-resident schedule (0 = eager mode: host draws per call)
+        self._sched_pos = 0   # entries consumed so far (host mirror of the device cursor)
         self._rand_step = 0
         self._two_mask = 0
         self._two_threshold = int(self._lib.ml2048_two_threshold(self._two_prob))
@@ -272,7 +277,6 @@ class VecGame:
         a.invalid = self._p(self._invalid)
         a.merged = self._p(self._merged)
         a.onehot_out = self._p(self._onehot)
-        a.randperm_keys = self._p(self._randkeys_dev)
         a.two_threshold = self._two_threshold
         a.stats = self._p(self._stats_dev)
         p = self._prep_args
@@ -289,7 +293,6 @@ class VecGame:
         p.invalid = self._p(self._invalid)
         p.merged = self._p(self._merged)
         p.onehot = self._p(self._onehot)
-        p.randperm = self._p(self._randperm_dev)
         p.two_threshold = self._two_threshold
         p.game_count = self._p(self._game_count_dev)
         p.id_offset = None
@@ -337,8 +340,80 @@ class VecGame:
         _lib.check(self._lib.ml2048_pack_randperm_keys(self._randperm.ctypes.data, self._tables_host[1].ctypes.data, RAND_ROWS),
                    "ml2048_pack_randperm_keys")
         self._tables_host[0] = self._randperm
-        self._tables_dev.copy_(torch.from_numpy(self._tables_host))
+        self._table_slot = 0
+        self._tables_dev[0].copy_(torch.from_numpy(self._tables_host))
         self._two_mask = int(self._lib.ml2048_two_mask(self._randfloat.ctypes.data, self._two_prob))
+
+    _TABLE_BYTES = 2 * RAND_ROWS * 16  # one slot of the table ring
+
+    def _table_ptrs(self) -> tuple[int, int]:
+        """(randperm, randperm_keys) device pointers of the slot eager calls use (slot 0 in scheduled mode:
+        the kernels add entry.table * table_stride themselves)."""
+        base = self._tables_dev.data_ptr() + (0 if self._sched_len else self._table_slot * self._TABLE_BYTES)
+        return base, base + RAND_ROWS * 16
+
+    # ------------------------------------------------------------------------------------------
+    # device-resident schedule (CUDA-graph replay without host work)
+    # ------------------------------------------------------------------------------------------
+
+    def schedule_ahead(self, steps: int, *, min_steps: int = 1) -> int:
+        """Pre-draw the host random numbers of the next ``steps`` runner steps (one prepare() + one step()
+        each) and keep them on the device, so that prepare()/step() stop touching the host generator and a
+        CUDA graph can replay them.  The draws are the reference's, in the reference's order
+        (game_numba.py:622-626 then :670 per runner step); every table refresh inside the window takes one
+        slot of the table ring.  Returns the number of steps scheduled.  ``steps = 0`` returns to eager mode."""
+        if self._sched_len and self._sched_pos < self._sched_len:
+            raise RuntimeError(f"{self._sched_len - self._sched_pos} scheduled steps are still pending")
+        if steps <= 0:
+            self._sched_len = self._sched_pos = 0
+            self._upload_tables()
+            return 0
+        slots = max(int(min_steps) + 1, min(steps + 1, 64))
+        if slots > self._table_slots:
+            self._table_slots = slots
+            self._tables_dev = torch.zeros((slots, 2, RAND_ROWS, 16), dtype=torch.uint8, device=self.device)
+        ring = np.zeros((slots, 2, RAND_ROWS, 16), dtype=np.uint8)
+
+        def put(slot: int) -> None:
+            ring[slot, 0] = self._randperm
+            _lib.check(self._lib.ml2048_pack_randperm_keys(self._randperm.ctypes.data, ring[slot, 1].ctypes.data, RAND_ROWS),
+                       "ml2048_pack_randperm_keys")
+            self._two_mask = int(self._lib.ml2048_two_mask(self._randfloat.ctypes.data, self._two_prob))
+
+        put(0)  # the tables in force now
+        slot = 0
+        entries = np.zeros((steps, 4), dtype=np.int64)
+        n = 0
+        while n < steps:
+            coin = self._draw_coin()  # game_numba.py:622
+            refresh = coin >= 0.9 or self._rand_step >= self._RAND_SIZE
+            if refresh and slot + 1 >= slots:
+                self._pending_coin = coin  # no ring slot left: this coin opens the next window
+                break
+            if refresh:
+                self._rand_step = 0
+                self._schedule.refresh_tables(self._randperm, self._randfloat)
+                slot += 1
+                put(slot)
+            off_prepare = self._schedule.offset()
+            off_step = self._schedule.offset()
+            entries[n, 0] = self._rand_step + off_prepare
+            entries[n, 1] = self._rand_step + off_step
+            entries[n, 2] = self._philox_counter
+            entries[n, 3] = self._two_mask | (slot << 32)
+            self._philox_counter += 2
+            self._rand_step += 1
+            n += 1
+        if n < min_steps:
+            raise RuntimeError(f"could only schedule {n} < {min_steps} steps with {slots} table slots")
+        self._tables_dev[: slot + 1].copy_(torch.from_numpy(ring[: slot + 1]))
+        self._table_slot = slot  # where the tables in force at the end of the window live
+        if self._sched_dev is None or self._sched_dev.shape[0] < steps:
+            self._sched_dev = torch.zeros((steps, 4), dtype=torch.int64, device=self.device)  # fixed address from here on
+        self._sched_dev[:n].copy_(torch.from_numpy(entries[:n]))
+        self._sched_cursor_dev.zero_()
+        self._sched_len, self._sched_pos = n, 0
+        return n
 
     # ------------------------------------------------------------------------------------------
     # reference surface
@@ -347,6 +422,8 @@ class VecGame:
     def reset(self, seed: Optional[int] = None, *, schedule: Any = None) -> None:
         """game_numba.py:606-617.  ``schedule`` (optional) replaces the numpy generator by recorded draws."""
         self._schedule = schedule if schedule is not None else NumpySchedule(seed)
+        self._sched_len = self._sched_pos = 0
+        self._pending_coin = None
         self._rand_step = 0
         self._randperm[:, :] = np.arange(16).reshape((1, 16))
         self._schedule.refresh_tables(self._randperm, self._randfloat)
@@ -378,21 +455,29 @@ class VecGame:
     def prepare(self):
         """game_numba.py:619-658: refresh tables with probability 0.1, draw an offset, reset every
         terminated slot in ascending order.  Returns ``(indices,)``."""
-        if self._schedule.refresh_coin() >= 0.9 or self._rand_step >= self._RAND_SIZE:
-            self._rand_step = 0
-            self._schedule.refresh_tables(self._randperm, self._randfloat)
-            self._upload_tables()
-        rand_offset = self._schedule.offset()
-
         p = self._prep_args
         cur = self._cur
+        if self._sched_len and self._sched_pos >= self._sched_len:
+            self.schedule_ahead(self._sched_len)  # window used up: draw the next one (eager callers only)
+        if self._sched_len:
+            p.sched = self._sched_dev.data_ptr()
+            p.sched_cursor = self._sched_cursor_dev.data_ptr() + 8 * cur
+            p.table_stride = self._TABLE_BYTES
+        else:
+            if self._draw_coin() >= 0.9 or self._rand_step >= self._RAND_SIZE:
+                self._rand_step = 0
+                self._schedule.refresh_tables(self._randperm, self._randfloat)
+                self._upload_tables()
+            rand_offset = self._schedule.offset()
+            p.sched = None
+            p.rand_base = self._rand_step + rand_offset
+            p.two_mask = self._two_mask
+            p.philox_counter = self._philox_counter
+            self._philox_counter += 1
         p.board = self._p(self._board[cur])
         p.valid = self._p(self._valid[cur])
-        p.rand_base = self._rand_step + rand_offset
-        p.two_mask = self._two_mask
+        p.randperm = self._table_ptrs()[0]
         p.philox_seed = self._philox_seed
-        p.philox_counter = self._philox_counter
-        self._philox_counter += 1
         stream = self._stream()
         with torch.cuda.device(self.device):
             if self._dist_group is None:
@@ -409,18 +494,22 @@ class VecGame:
             return (np.zeros((0,), dtype=np.int64),)
         return (idx.cpu().numpy(),)
 
+    def _draw_coin(self) -> float:
+        coin = getattr(self, "_pending_coin", None)
+        if coin is not None:
+            self._pending_coin = None
+            return coin
+        return self._schedule.refresh_coin()
+
     def step(self, actions) -> VecStepResult:
         """game_numba.py:660-698.  ``actions``: (M,) integers in 0..3 (NumPy array, CPU or CUDA tensor)."""
         assert tuple(actions.shape) == (self._size,), actions.shape  # game_numba.py:668
-        rand_offset = self._schedule.offset()  # :670
-
         a = self._step_args
         dev_actions, a.action_dtype = self._stage_actions(actions)
         a.action_mode = _lib.ACTIONS_GIVEN
         a.actions = dev_actions.data_ptr()
         a.actions_out = None
-        self._launch_step(self._rand_step + rand_offset)
-        self._rand_step += 1  # :685
+        self._launch_step()
         self._keepalive = dev_actions
         return VecStepResult(self)
 
@@ -463,28 +552,39 @@ class VecGame:
     def step_random(self, *, return_actions: bool = False):
         """One step with uniformly random VALID actions chosen inside the kernel (Philox) --
         the benchmark policy (semantics of policy/random.py:17-27), no action array crosses the bus."""
-        rand_offset = self._schedule.offset()
         a = self._step_args
         a.action_mode = _lib.ACTIONS_RANDOM_VALID
         a.action_dtype = _lib.ACT_U8
         a.actions = None
         a.actions_out = self._p(self._actions_out) if return_actions else None
-        self._launch_step(self._rand_step + rand_offset)
-        self._rand_step += 1
+        self._launch_step()
         return VecStepResult(self)
 
-    def _launch_step(self, rand_seed: int) -> None:
+    def _launch_step(self) -> None:
         a = self._step_args
         cur = self._cur
+        if self._sched_len:
+            if self._sched_pos >= self._sched_len:
+                raise RuntimeError("the device schedule is used up: call prepare() (or schedule_ahead) first")
+            a.sched = self._sched_dev.data_ptr()
+            a.sched_cursor = self._sched_cursor_dev.data_ptr() + 8 * cur
+            a.sched_cursor_next = self._sched_cursor_dev.data_ptr() + 8 * (1 - cur)
+            a.table_stride = self._TABLE_BYTES
+            self._sched_pos += 1
+        else:
+            rand_offset = self._schedule.offset()  # game_numba.py:670
+            a.sched = None
+            a.rand_seed = self._rand_step + rand_offset  # :681
+            self._rand_step += 1  # :685
+            a.two_mask = self._two_mask
+            a.philox_counter = self._philox_counter
+            self._philox_counter += 1
         a.board_in = self._p(self._board[cur])
         a.board_out = self._p(self._board[1 - cur])
         a.valid_in = self._p(self._valid[cur])
         a.valid_out = self._p(self._valid[1 - cur])
-        a.rand_seed = rand_seed
-        a.two_mask = self._two_mask
+        a.randperm_keys = self._table_ptrs()[1]
         a.philox_seed = self._philox_seed
-        a.philox_counter = self._philox_counter
-        self._philox_counter += 1
         with torch.cuda.device(self.device):
             _lib.check(self._lib.ml2048_step(C.byref(a), self._stream()), "ml2048_step")
         self._cur = 1 - cur
@@ -539,7 +639,11 @@ class VecGame:
             "philox_seed": self._philox_seed,
             "philox_counter": self._philox_counter,
             "schedule": copy.deepcopy(self._schedule),
+            "table_slot": self._table_slot,
+            "pending_coin": getattr(self, "_pending_coin", None),
         }
+        if self._sched_len:
+            raise RuntimeError("state_dict() while a device schedule is active is not supported: call schedule_ahead(0) first")
         return {"tensors": tensors, "host": host}
 
     def load_state_dict(self, sd: dict[str, Any]) -> None:
@@ -552,6 +656,10 @@ class VecGame:
             dst = getattr(self, name)
             if dst is None:
                 raise ValueError(f"snapshot has {name} but this environment does not track it")
+            if name == "_tables_dev" and dst.shape != t.shape:
+                self._tables_dev = t.clone()
+                self._table_slots = t.shape[0]
+                continue
             dst.copy_(t)
         self._cur = host["cur"]
         self._rand_step = host["rand_step"]
@@ -561,6 +669,9 @@ class VecGame:
         self._philox_seed = host["philox_seed"]
         self._philox_counter = host["philox_counter"]
         self._schedule = copy.deepcopy(host["schedule"])
+        self._table_slot = host.get("table_slot", 0)
+        self._pending_coin = host.get("pending_coin")
+        self._sched_len = self._sched_pos = 0
 
     def episode_stats(self, *, reset: bool = False) -> dict[str, Any]:
         """Finished-episode statistics accumulated by step(): RunnerStats' max-tile histogram
@@ -595,6 +706,59 @@ class VecGame:
         self._id_offset_dev.copy_(self._counts_all[: self._dist_rank].sum().reshape(1))
         _lib.check(self._lib.ml2048_prepare_apply(C.byref(p), stream), "ml2048_prepare_apply")
         self._game_count_dev += self._counts_all.sum()
+
+
+class GraphedRollout:
+    """``steps`` runner steps (prepare + step each) captured once as a CUDA graph and replayed with one launch.
+
+    The per-step host random numbers come from the device-resident schedule (``VecGame.schedule_ahead``), so a
+    replay involves no host work besides the graph launch; the schedule window is refilled between replays when
+    it runs low.  ``steps`` must be even (boards and masks are ping-pong buffers: an even number of steps ends in
+    the buffers the graph started from).  Policy: uniform over valid actions, chosen in-kernel
+    (``actions=None``), or a caller-owned CUDA tensor of actions that the caller rewrites between replays of a
+    ONE-step-pair graph (``actions=tensor``, read by every captured step)."""
+
+    def __init__(self, env: VecGame, steps: int, *, window: Optional[int] = None, actions: Optional[torch.Tensor] = None,
+                 return_actions: bool = False):
+        if steps <= 0 or steps % 2:
+            raise ValueError(f"steps={steps}: must be a positive even number")
+        self.env, self.steps = env, int(steps)
+        self.window = int(window) if window else self.steps * 16
+        if self.window < self.steps:
+            raise ValueError("window must cover at least one replay")
+        env.configure(sync_free=True)
+        if env._sched_len and env._sched_pos < env._sched_len:
+            raise RuntimeError("the environment already has a pending device schedule")
+        env.schedule_ahead(self.window, min_steps=self.steps)
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=env.device)
+        side.wait_stream(torch.cuda.current_stream(env.device))
+        pos, cur = env._sched_pos, env._cur
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(self.graph, stream=side):
+                for _ in range(self.steps):
+                    env.prepare()
+                    if actions is None:
+                        env.step_random(return_actions=return_actions)
+                    else:
+                        env.step(actions)
+        torch.cuda.current_stream(env.device).wait_stream(side)
+        # capturing executed nothing on the device: rewind the host mirrors
+        env._sched_pos = pos
+        assert env._cur == cur
+
+    def replay(self, times: int = 1) -> None:
+        env = self.env
+        for _ in range(times):
+            if env._sched_pos + self.steps > env._sched_len:
+                if env._sched_pos < env._sched_len:
+                    # a partial tail cannot feed a whole replay: run it eagerly, then refill
+                    while env._sched_pos < env._sched_len:
+                        env.prepare()
+                        env.step_random()
+                env.schedule_ahead(self.window, min_steps=self.steps)
+            self.graph.replay()
+            env._sched_pos += self.steps
 
 
 def stats_to_dict(raw: torch.Tensor) -> dict[str, Any]:

@@ -453,3 +453,57 @@ def test_properties_at_bench_size(ml):
     assert torch.equal(res["invalid"] != 0, has_bad)
     assert torch.equal(res["state"][has_bad], board[has_bad])
     assert torch.equal(env._score[has_bad], score[has_bad])
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident schedule and CUDA-graph replay
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("fname,window", [("rollout_c1_seed0_normal.npz", 64), ("rollout_tiny_long.npz", 40),
+                                          ("rollout_ragged_rank.npz", 7)])
+def test_scheduled_mode_matches_reference_golden(ml, fname, window):
+    """prepare()/step() fed from the pre-drawn device schedule (no host draws per call) reproduce the
+    reference rollouts bit for bit, across window refills and table-ring exhaustion."""
+    g = golden(fname)
+    m, n, seed, aseed = [int(x) for x in g["meta"]]
+    two_prob, wild = [float(x) for x in g["meta_f"]]
+    env = _make(ml, m, str(g["reward_kind"]), two_prob=two_prob)
+    env.reset(seed)
+    assert env.schedule_ahead(window) >= 1
+    got = record_rollout(env, n, action_seed=aseed, wild=wild, full=True)
+    compare_rollouts(got, g)
+
+
+def test_leaving_scheduled_mode_continues_the_same_stream(ml):
+    g = golden("rollout_c1_seed0_normal.npz")
+    m, n, seed, aseed = [int(x) for x in g["meta"]]
+    env = _make(ml, m, "normal")
+    env.reset(seed)
+    env.schedule_ahead(20)
+    a = record_rollout(env, 20, actions=g["actions"][:20], full=True)
+    env.schedule_ahead(0)  # back to per-call host draws
+    b = record_rollout(env, n - 20, actions=g["actions"][20:], full=True)
+    for k in ("state", "reward", "score", "id", "terminated", "valid_actions"):
+        np.testing.assert_array_equal(np.concatenate([a[k], b[k]]), g[k], err_msg=k)
+
+
+@pytest.mark.parametrize("m,steps,replays", [(2048, 16, 12), (100000, 2, 40)])
+def test_graph_replay_equals_eager_rollout(ml, m, steps, replays):
+    eager = _make(ml, m, "improved", output="torch", onehot="f32", sync_free=True)
+    eager.reset(5)
+    for _ in range(steps * replays):
+        eager.prepare()
+        eager.step_random()
+    env = _make(ml, m, "improved", output="torch", onehot="f32", sync_free=True)
+    env.reset(5)
+    roll = ml.GraphedRollout(env, steps, window=steps * 5)
+    roll.replay(replays)
+    torch.cuda.synchronize()
+    assert torch.equal(env.observations()[0], eager.observations()[0])
+    assert torch.equal(env.observations()[1], eager.observations()[1])
+    assert torch.equal(env._score, eager._score)
+    assert torch.equal(env._id, eager._id)
+    assert torch.equal(env.observations_onehot(), eager.observations_onehot())
+    assert env._game_count == eager._game_count
+    assert torch.equal(env.episode_stats_tensor(), eager.episode_stats_tensor())
