@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ML2048_ABI_VERSION 3
+#define ML2048_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define ML2048_API __attribute__((visibility("default")))
@@ -137,6 +137,17 @@ typedef struct {
     const int64_t *sched_cursor;   /* device scalar: index of the entry to use */
     int64_t *sched_cursor_next;    /* device scalar (not aliasing sched_cursor) or null: receives *sched_cursor + 1 */
     int64_t table_stride;          /* bytes between consecutive slots of the table ring (randperm_keys = slot 0) */
+
+    /* per-episode record keyed by GAME ID (or null): when the game with id in [episode_id_base,
+     * episode_id_base + episode_capacity) finishes, its final step count, score and max tile exponent are stored
+     * at index id - episode_id_base.  This is what eval_perf.py gathers through ReplayRecorder for the games
+     * with `buffer.id < rounds` (eval_perf.py:80-102, replay.py:110-232) without any per-step host loop. */
+    const int32_t *id;             /* [num_games] game ids (the array ml2048_prepare maintains) */
+    int64_t episode_id_base;
+    int64_t episode_capacity;
+    int32_t *episode_steps;        /* [episode_capacity] */
+    float *episode_score;          /* [episode_capacity] */
+    uint8_t *episode_max_tile;     /* [episode_capacity]; 0 = not finished yet */
 } ml2048_step_args;
 
 /* Arguments of the auto-reset.  Replaces the host loop of VecGame.prepare (game_numba.py:629-658):

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libml2048_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 STATS_REPLICAS = 64
 STATS_WORDS = 24  # 20 histogram bins + episodes, score_sum, step_sum, score_max (unsigned long long each)
 
@@ -61,6 +61,12 @@ class StepArgs(C.Structure):
         ("sched_cursor", C.c_void_p),
         ("sched_cursor_next", C.c_void_p),
         ("table_stride", C.c_int64),
+        ("id", C.c_void_p),
+        ("episode_id_base", C.c_int64),
+        ("episode_capacity", C.c_int64),
+        ("episode_steps", C.c_void_p),
+        ("episode_score", C.c_void_p),
+        ("episode_max_tile", C.c_void_p),
     ]
 
 

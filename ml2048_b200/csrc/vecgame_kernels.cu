@@ -230,6 +230,15 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_ar
                 fusion_log(f, m0, m1, m2, m3);
                 reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(m0, m1, m2, m3);
             }
+            if (dead && a.episode_max_tile) {
+                // eval_perf.py semantics: episodes are keyed by game id, not by finishing order
+                const int64_t e = (int64_t)a.id[g] - a.episode_id_base;
+                if (e >= 0 && e < a.episode_capacity) {
+                    a.episode_steps[e] = nstep;
+                    a.episode_score[e] = score;
+                    a.episode_max_tile[e] = (uint8_t)max_cell(r0, r1, r2, r3);
+                }
+            }
             if (dead && a.stats) {
                 // finished-episode statistics (RunnerStats, runner.py:158-166): rare (~1% of moves)
                 ml2048_stats *st = a.stats + (blockIdx.x % ML2048_STATS_REPLICAS);
@@ -531,6 +540,7 @@ int ml2048_step(const ml2048_step_args *args, void *stream)
         return ML2048_E_ENUM;
     }
     if (a.onehot_out && (a.onehot_dtype < ML2048_ONEHOT_F32 || a.onehot_dtype > ML2048_ONEHOT_U8)) return ML2048_E_ENUM;
+    if (a.episode_max_tile && (!a.id || !a.episode_steps || !a.episode_score || a.episode_capacity <= 0)) return ML2048_E_NULL;
     if (a.sched) {
         if (!a.sched_cursor || a.sched_cursor == a.sched_cursor_next) return ML2048_E_NULL;
         if (misaligned(a.sched, 8) || misaligned(a.sched_cursor, 8) || misaligned(a.sched_cursor_next, 8) || (a.table_stride & 15))

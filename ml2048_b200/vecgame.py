@@ -229,6 +229,12 @@ class VecGame:
             self._stats_dev = torch.zeros((_lib.STATS_REPLICAS, _lib.STATS_WORDS), dtype=torch.int64, device=dev)
         self._cur = 0
         self._host: dict[str, torch.Tensor] = {}  # pinned staging buffers, one per fetched field
+        self._dev_index = self.device.index
+        self._guard = VecGame._DeviceGuard(self._dev_index)
+        # raw pointers of the ping-pong buffers (creating tensor views per call costs microseconds)
+        self._board_ptr = (self._board[0].data_ptr(), self._board[1].data_ptr())
+        self._valid_ptr = (self._valid[0].data_ptr(), self._valid[1].data_ptr())
+        self._cursor_ptr = (self._sched_cursor_dev.data_ptr(), self._sched_cursor_dev.data_ptr() + 8)
 
         # host copies of the random tables, as in the reference (game_numba.py:577-580)
         self._randperm = np.empty((RAND_ROWS, 16), dtype=np.uint8)
@@ -260,7 +266,27 @@ class VecGame:
         return None if t is None else t.data_ptr()
 
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
+
+    class _DeviceGuard:
+        """Cheap `with torch.cuda.device(...)`: does nothing when the environment's device is already current."""
+
+        __slots__ = ("_want", "_prev")
+
+        def __init__(self, index: int):
+            self._want = index
+            self._prev = -1
+
+        def __enter__(self):
+            cur = torch.cuda.current_device()
+            if cur != self._want:
+                self._prev = cur
+                torch.cuda.set_device(self._want)
+
+        def __exit__(self, *exc):
+            if self._prev >= 0:
+                torch.cuda.set_device(self._prev)
+                self._prev = -1
 
     def _init_args(self) -> None:
         a = self._step_args
@@ -461,7 +487,7 @@ class VecGame:
             self.schedule_ahead(self._sched_len)  # window used up: draw the next one (eager callers only)
         if self._sched_len:
             p.sched = self._sched_dev.data_ptr()
-            p.sched_cursor = self._sched_cursor_dev.data_ptr() + 8 * cur
+            p.sched_cursor = self._cursor_ptr[cur]
             p.table_stride = self._TABLE_BYTES
         else:
             if self._draw_coin() >= 0.9 or self._rand_step >= self._RAND_SIZE:
@@ -474,12 +500,12 @@ class VecGame:
             p.two_mask = self._two_mask
             p.philox_counter = self._philox_counter
             self._philox_counter += 1
-        p.board = self._p(self._board[cur])
-        p.valid = self._p(self._valid[cur])
+        p.board = self._board_ptr[cur]
+        p.valid = self._valid_ptr[cur]
         p.randperm = self._table_ptrs()[0]
         p.philox_seed = self._philox_seed
         stream = self._stream()
-        with torch.cuda.device(self.device):
+        with self._guard:
             if self._dist_group is None:
                 _lib.check(self._lib.ml2048_prepare(C.byref(p), stream), "ml2048_prepare")
             else:
@@ -567,8 +593,8 @@ class VecGame:
             if self._sched_pos >= self._sched_len:
                 raise RuntimeError("the device schedule is used up: call prepare() (or schedule_ahead) first")
             a.sched = self._sched_dev.data_ptr()
-            a.sched_cursor = self._sched_cursor_dev.data_ptr() + 8 * cur
-            a.sched_cursor_next = self._sched_cursor_dev.data_ptr() + 8 * (1 - cur)
+            a.sched_cursor = self._cursor_ptr[cur]
+            a.sched_cursor_next = self._cursor_ptr[1 - cur]
             a.table_stride = self._TABLE_BYTES
             self._sched_pos += 1
         else:
@@ -579,13 +605,13 @@ class VecGame:
             a.two_mask = self._two_mask
             a.philox_counter = self._philox_counter
             self._philox_counter += 1
-        a.board_in = self._p(self._board[cur])
-        a.board_out = self._p(self._board[1 - cur])
-        a.valid_in = self._p(self._valid[cur])
-        a.valid_out = self._p(self._valid[1 - cur])
+        a.board_in = self._board_ptr[cur]
+        a.board_out = self._board_ptr[1 - cur]
+        a.valid_in = self._valid_ptr[cur]
+        a.valid_out = self._valid_ptr[1 - cur]
         a.randperm_keys = self._table_ptrs()[1]
         a.philox_seed = self._philox_seed
-        with torch.cuda.device(self.device):
+        with self._guard:
             _lib.check(self._lib.ml2048_step(C.byref(a), self._stream()), "ml2048_step")
         self._cur = 1 - cur
 
@@ -672,6 +698,30 @@ class VecGame:
         self._table_slot = host.get("table_slot", 0)
         self._pending_coin = host.get("pending_coin")
         self._sched_len = self._sched_pos = 0
+
+    def enable_episode_log(self, capacity: int, id_base: int = 0) -> None:
+        """Record (steps, score, max tile) of every finished game whose id lies in [id_base, id_base+capacity),
+        indexed by id -- the statistic eval_perf.py collects for the games with ``id < rounds``
+        (eval_perf.py:80-102) -- inside the step kernel, with no per-step host work."""
+        if capacity <= 0:
+            raise ValueError(f"capacity={capacity}")
+        dev = self.device
+        self._ep_steps = torch.zeros((capacity,), dtype=torch.int32, device=dev)
+        self._ep_score = torch.zeros((capacity,), dtype=torch.float32, device=dev)
+        self._ep_max_tile = torch.zeros((capacity,), dtype=torch.uint8, device=dev)
+        a = self._step_args
+        a.id = self._p(self._id)
+        a.episode_id_base = int(id_base)
+        a.episode_capacity = int(capacity)
+        a.episode_steps = self._p(self._ep_steps)
+        a.episode_score = self._p(self._ep_score)
+        a.episode_max_tile = self._p(self._ep_max_tile)
+
+    def episode_log(self) -> dict[str, torch.Tensor]:
+        """Device tensors indexed by (game id - id_base): ``steps`` i32, ``score`` f32, ``max_tile`` u8 (0 = unfinished)."""
+        if getattr(self, "_ep_max_tile", None) is None:
+            raise RuntimeError("call enable_episode_log(capacity) first")
+        return {"steps": self._ep_steps, "score": self._ep_score, "max_tile": self._ep_max_tile}
 
     def episode_stats(self, *, reset: bool = False) -> dict[str, Any]:
         """Finished-episode statistics accumulated by step(): RunnerStats' max-tile histogram

@@ -507,3 +507,31 @@ def test_graph_replay_equals_eager_rollout(ml, m, steps, replays):
     assert torch.equal(env.observations_onehot(), eager.observations_onehot())
     assert env._game_count == eager._game_count
     assert torch.equal(env.episode_stats_tensor(), eager.episode_stats_tensor())
+
+
+def test_episode_log_by_game_id(ml, oracle):
+    """The in-kernel episode log (eval_perf.py semantics: keyed by game id) against the same log built on the
+    host from the oracle's per-step results."""
+    m, n, rounds = 500, 700, 900
+    ref = oracle.OracleVecGame(m)
+    ref.reset(4)
+    env = _make(ml, m)
+    env.reset(4)
+    env.enable_episode_log(rounds)
+    want = {"steps": np.zeros(rounds, np.int32), "score": np.zeros(rounds, np.float32), "max_tile": np.zeros(rounds, np.uint8)}
+    rng = np.random.default_rng(1)
+    for _ in range(n):
+        ref.prepare()
+        env.prepare()
+        acts = oracle.random_valid_actions(ref.observations()[1], rng.random(m))
+        res = ref.step(acts)
+        env.step(acts)
+        ids = ref._data["id"]
+        done = (res["terminated"] != 0) & (res["invalid"] == 0) & (ids < rounds)
+        want["steps"][ids[done]] = res["step"][done]
+        want["score"][ids[done]] = res["score"][done]
+        want["max_tile"][ids[done]] = res["state"][done].max(axis=1)
+    log = env.episode_log()
+    assert (want["max_tile"] > 0).sum() > 600
+    for k in want:
+        np.testing.assert_array_equal(log[k].cpu().numpy(), want[k], err_msg=k)
