@@ -410,6 +410,10 @@ class VecGame:
         slot = 0
         entries = np.zeros((steps, 4), dtype=np.int64)
         n = 0
+        while n < steps and self._rng_mode != _lib.RNG_REPLAY:
+            entries[n, 2] = self._philox_counter  # Philox mode: the counter is the whole schedule
+            self._philox_counter += 2
+            n += 1
         while n < steps:
             coin = self._draw_coin()  # game_numba.py:622
             refresh = coin >= 0.9 or self._rand_step >= self._RAND_SIZE
@@ -490,11 +494,13 @@ class VecGame:
             p.sched_cursor = self._cursor_ptr[cur]
             p.table_stride = self._TABLE_BYTES
         else:
-            if self._draw_coin() >= 0.9 or self._rand_step >= self._RAND_SIZE:
-                self._rand_step = 0
-                self._schedule.refresh_tables(self._randperm, self._randfloat)
-                self._upload_tables()
-            rand_offset = self._schedule.offset()
+            rand_offset = 0
+            if self._rng_mode == _lib.RNG_REPLAY:  # Philox spawns need none of the reference's host draws
+                if self._draw_coin() >= 0.9 or self._rand_step >= self._RAND_SIZE:
+                    self._rand_step = 0
+                    self._schedule.refresh_tables(self._randperm, self._randfloat)
+                    self._upload_tables()
+                rand_offset = self._schedule.offset()
             p.sched = None
             p.rand_base = self._rand_step + rand_offset
             p.two_mask = self._two_mask
@@ -598,7 +604,7 @@ class VecGame:
             a.table_stride = self._TABLE_BYTES
             self._sched_pos += 1
         else:
-            rand_offset = self._schedule.offset()  # game_numba.py:670
+            rand_offset = self._schedule.offset() if self._rng_mode == _lib.RNG_REPLAY else 0  # game_numba.py:670
             a.sched = None
             a.rand_seed = self._rand_step + rand_offset  # :681
             self._rand_step += 1  # :685

@@ -8,8 +8,8 @@ import torch
 
 import ml2048_b200
 
-for sched in (0, 256):
-    env = ml2048_b200.VecGame(2048, output="torch", onehot="f32", track_merged=False, sync_free=True)
+for sched, rng in ((0, 'replay'), (256, 'replay'), (0, 'philox')):
+    env = ml2048_b200.VecGame(2048, output="torch", onehot="f32", track_merged=False, sync_free=True, rng_mode=rng)
     env.reset(0)
     if sched:
         env.schedule_ahead(sched)
@@ -19,15 +19,17 @@ for sched in (0, 256):
         env.step_random()
     torch.cuda.synchronize()
     n = 2000
-    t0 = time.perf_counter()
-    for _ in range(n):
+    tp = ts = ta = 0.0
+    for i in range(n):
+        t0 = time.perf_counter()
         env.prepare()
-    t1 = time.perf_counter()
-    for _ in range(n):
-        env.step_random()
-    t2 = time.perf_counter()
-    for _ in range(n):
-        env.step(acts)
-    t3 = time.perf_counter()
+        t1 = time.perf_counter()
+        if i % 2:
+            env.step_random()
+            ts += time.perf_counter() - t1
+        else:
+            env.step(acts)
+            ta += time.perf_counter() - t1
+        tp += t1 - t0
     torch.cuda.synchronize()
-    print(f"schedule_ahead={sched}: prepare {(t1-t0)/n*1e6:.1f} us, step_random {(t2-t1)/n*1e6:.1f} us, step(actions) {(t3-t2)/n*1e6:.1f} us per call (host)")
+    print(f"rng={rng} schedule_ahead={sched}: prepare {tp/n*1e6:.1f} us, step_random {ts/(n/2)*1e6:.1f} us, step(actions) {ta/(n/2)*1e6:.1f} us per call (host, refills included)")
