@@ -349,9 +349,10 @@ def run_b200_arm(args: argparse.Namespace) -> None:
 
         def e2e_step(t: int) -> int:
             (idx,) = env.prepare()                # D2H: reset count + indices
-            res = env.step(host_actions[t])       # H2D: M action bytes
+            keys = ("state", "valid_actions", "reward", "terminated")  # D2H: what a rollout consumer reads
+            res = env.step(host_actions[t], fetch=keys)  # H2D: M action bytes
             got = 0
-            for key in ("state", "valid_actions", "reward", "terminated"):  # D2H: what a rollout consumer reads
+            for key in keys:
                 got += res[key].nbytes
             return got + idx.nbytes + 8
 

@@ -533,9 +533,15 @@ class VecGame:
             return coin
         return self._schedule.refresh_coin()
 
-    def step(self, actions) -> VecStepResult:
-        """game_numba.py:660-698.  ``actions``: (M,) integers in 0..3 (NumPy array, CPU or CUDA tensor)."""
+    def step(self, actions, *, fetch: Optional[tuple] = None) -> VecStepResult:
+        """game_numba.py:660-698.  ``actions``: (M,) integers in 0..3 (NumPy array, CPU or CUDA tensor).
+
+        ``fetch`` (NumPy mode, host actions): result keys the caller is going to read.  For large batches the
+        step then runs as a pipeline over slices of the games -- actions H2D, kernel, results D2H on three
+        streams -- so the PCIe copies in both directions overlap the kernel instead of following it."""
         assert tuple(actions.shape) == (self._size,), actions.shape  # game_numba.py:668
+        if fetch and self._can_pipeline(actions):
+            return self._step_pipelined(actions, tuple(fetch))
         a = self._step_args
         dev_actions, a.action_dtype = self._stage_actions(actions)
         a.action_mode = _lib.ACTIONS_GIVEN
@@ -620,6 +626,94 @@ class VecGame:
         with self._guard:
             _lib.check(self._lib.ml2048_step(C.byref(a), self._stream()), "ml2048_step")
         self._cur = 1 - cur
+
+    # -- host-buffer pipeline -----------------------------------------------------------------------
+
+    _PIPELINE_MIN_GAMES = 1 << 18
+    _PIPELINE_CHUNKS = 8
+
+    def _can_pipeline(self, actions) -> bool:
+        if self._output != "numpy" or self._sched_len or self._size < self._PIPELINE_MIN_GAMES:
+            return False
+        if isinstance(actions, np.ndarray):
+            return actions.dtype in (np.int64, np.int32, np.uint8, np.int8)
+        return isinstance(actions, torch.Tensor) and actions.device.type == "cpu" and actions.dtype in (
+            torch.int64, torch.int32, torch.uint8, torch.int8)
+
+    def _step_pipelined(self, actions, fetch: tuple) -> VecStepResult:
+        if isinstance(actions, np.ndarray):
+            actions = torch.from_numpy(np.ascontiguousarray(actions))
+        actions = actions.contiguous()
+        code = {torch.int64: _lib.ACT_I64, torch.int32: _lib.ACT_I32, torch.uint8: _lib.ACT_U8, torch.int8: _lib.ACT_U8}[actions.dtype]
+        m = self._size
+        if getattr(self, "_pipe_streams", None) is None:
+            self._pipe_streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+            self._pipe_actions = {}
+        h2d, d2h = self._pipe_streams
+        dev_actions = self._pipe_actions.get(actions.dtype)
+        if dev_actions is None:
+            dev_actions = torch.empty((m,), dtype=actions.dtype, device=self.device)
+            self._pipe_actions[actions.dtype] = dev_actions
+        main = torch.cuda.current_stream(self.device)
+        cur = self._cur
+        # the host draws of this step, once (game_numba.py:670, :681, :685)
+        rand_offset = self._schedule.offset() if self._rng_mode == _lib.RNG_REPLAY else 0
+        rand_seed = self._rand_step + rand_offset
+        self._rand_step += 1
+        counter = self._philox_counter
+        self._philox_counter += 1
+        self._cur = 1 - cur  # so that _device_field() names the post-step buffers
+        fields = {k: self._device_field(k) for k in fetch}
+        host = {}
+        for k, t in fields.items():
+            buf = self._host.get(k)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                self._host[k] = buf
+            host[k] = buf
+        a = _lib.StepArgs.from_buffer_copy(self._step_args)
+        a.action_mode, a.action_dtype, a.actions_out, a.sched = _lib.ACTIONS_GIVEN, code, None, None
+        a.rand_seed, a.two_mask, a.philox_counter, a.philox_seed = rand_seed, self._two_mask, counter, self._philox_seed
+        a.randperm_keys = self._table_ptrs()[1]
+        esz = actions.element_size()
+        per = -(-m // self._PIPELINE_CHUNKS)
+        per = (per + 255) // 256 * 256
+        h2d.wait_stream(main)
+        d2h.wait_stream(main)
+        raw_main = main.cuda_stream
+        with self._guard:
+            for lo in range(0, m, per):
+                hi = min(m, lo + per)
+                with torch.cuda.stream(h2d):
+                    dev_actions[lo:hi].copy_(actions[lo:hi], non_blocking=True)
+                main.wait_stream(h2d)
+                a.num_games = hi - lo
+                a.slot_base = self._slot_base + lo
+                a.board_in = self._board_ptr[cur] + 16 * lo
+                a.board_out = self._board_ptr[1 - cur] + 16 * lo
+                a.valid_in = self._valid_ptr[cur] + 4 * lo
+                a.valid_out = self._valid_ptr[1 - cur] + 4 * lo
+                a.actions = dev_actions.data_ptr() + esz * lo
+                a.step = self._step.data_ptr() + 4 * lo
+                a.score = self._score.data_ptr() + 4 * lo
+                a.reward = self._reward.data_ptr() + 4 * lo
+                a.terminated = self._terminated_padded.data_ptr() + lo
+                a.invalid = self._invalid.data_ptr() + lo
+                a.merged = None if self._merged is None else self._merged.data_ptr() + 16 * lo
+                if self._onehot is not None:
+                    a.onehot_out = self._onehot.data_ptr() + lo * 256 * self._onehot.element_size()
+                if self._step_args.id:
+                    a.id = self._id.data_ptr() + 4 * lo
+                _lib.check(self._lib.ml2048_step(C.byref(a), raw_main), "ml2048_step")
+                d2h.wait_stream(main)
+                with torch.cuda.stream(d2h):
+                    for k, t in fields.items():
+                        host[k][lo:hi].copy_(t[lo:hi], non_blocking=True)
+        d2h.synchronize()
+        res = VecStepResult(self)
+        for k in fetch:
+            dict.__setitem__(res, k, host[k].numpy())
+        return res
 
     def _stage_actions(self, actions) -> tuple[torch.Tensor, int]:
         if isinstance(actions, np.ndarray):

@@ -535,3 +535,28 @@ def test_episode_log_by_game_id(ml, oracle):
     assert (want["max_tile"] > 0).sum() > 600
     for k in want:
         np.testing.assert_array_equal(log[k].cpu().numpy(), want[k], err_msg=k)
+
+
+def test_pipelined_host_step_matches_plain_step(ml, oracle):
+    """step(host actions, fetch=...) runs as an H2D / kernel / D2H pipeline over slices of the games; results
+    must equal the one-shot step and the oracle."""
+    m = (1 << 18) + 777
+    ref = oracle.OracleVecGame(m, "improved")
+    ref.reset(2)
+    env = _make(ml, m, "improved", onehot="u8")
+    env.reset(2)
+    env.enable_episode_log(1000)
+    rng = np.random.default_rng(0)
+    keys = ("state", "valid_actions", "reward", "terminated", "prev_state", "merged", "score")
+    for t in range(12):
+        ref.prepare()
+        env.prepare()
+        acts = oracle.random_valid_actions(ref.observations()[1], rng.random(m))
+        r0 = ref.step(acts)
+        host_acts = torch.from_numpy(acts.astype(np.uint8 if t % 2 else np.int64)).pin_memory()
+        r1 = env.step(host_acts, fetch=keys)
+        assert all(dict.__contains__(r1, k) for k in keys), "fetched keys must be pre-populated"
+        for k in keys + ("step", "invalid", "prev_valid_actions"):
+            np.testing.assert_array_equal(r1[k], r0[k], err_msg=f"{k} step {t}")
+    oh = env.observations_onehot().cpu().numpy()
+    np.testing.assert_array_equal(oh, oracle.onehot(ref.observations()[0]).astype(np.uint8))
