@@ -421,38 +421,49 @@ def run_b200_arm(args: argparse.Namespace) -> None:
 
 
 def measure_extras(ml2048_b200, torch, dev, seed: int) -> dict:
-    """Secondary lines (not the headline): core-only path, Philox mode, the training-shape M = 2048."""
+    """Secondary lines (not the headline): core-only path, Philox mode, narrower one-hot types, and the
+    training shapes of run_train3.py (BASELINE configs[1]) replayed as a 16-step CUDA graph."""
     out = {}
 
-    def timed(env, n, warm=5):
-        for _ in range(warm):
-            env.prepare()
-            env.step_random()
+    def timed(env, n, graph_steps=0):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(n):
-            env.prepare()
-            env.step_random()
-        b.record()
+        if graph_steps:
+            roll = ml2048_b200.GraphedRollout(env, graph_steps, window=graph_steps * 16)
+            roll.replay(1)
+            torch.cuda.synchronize()
+            a.record()
+            roll.replay(n // graph_steps)
+            b.record()
+        else:
+            for _ in range(5):
+                env.prepare()
+                env.step_random()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(n):
+                env.prepare()
+                env.step_random()
+            b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n
 
-    for name, kw, m, n in (
-        ("core_only_replay_M2^24", dict(rng_mode="replay"), 1 << 24, 50),
-        ("core_only_philox_M2^24", dict(rng_mode="philox"), 1 << 24, 50),
-        ("fused_bf16_onehot_M2^24", dict(rng_mode="replay", onehot="bf16"), 1 << 24, 50),
-        ("fused_u8_onehot_M2^24", dict(rng_mode="replay", onehot="u8"), 1 << 24, 50),
-        ("train_shape_M2048_fused_f32", dict(rng_mode="replay", onehot="f32"), 2048, 200),
-        ("train_shape_M4096_fused_f32", dict(rng_mode="replay", onehot="f32"), 4096, 200),
+    for name, kw, m, n, graph_steps in (
+        ("core_only_replay_M2^24", dict(rng_mode="replay"), 1 << 24, 48, 0),
+        ("core_only_philox_M2^24", dict(rng_mode="philox"), 1 << 24, 48, 0),
+        ("fused_bf16_onehot_M2^24", dict(rng_mode="replay", onehot="bf16"), 1 << 24, 48, 0),
+        ("fused_u8_onehot_M2^24", dict(rng_mode="replay", onehot="u8"), 1 << 24, 48, 0),
+        ("train_shape_M2048_fused_f32_eager", dict(rng_mode="replay", onehot="f32"), 2048, 192, 0),
+        ("train_shape_M2048_fused_f32_graph16", dict(rng_mode="replay", onehot="f32"), 2048, 192, 16),
+        ("train_shape_M4096_fused_f32_graph16", dict(rng_mode="replay", onehot="f32"), 4096, 192, 16),
     ):
-        env = ml2048_b200.VecGame(m, output="torch", track_merged=False, sync_free=True, device=dev, **kw)
+        env = ml2048_b200.VecGame(m, ml2048_b200.reward_fn_improved if m < 100000 else None, output="torch",
+                                  track_merged=False, sync_free=True, device=dev, **kw)
         env.reset(seed)
         for _ in range(64 if m > 100000 else 128):
             env.prepare()
             env.step_random()
-        ms = timed(env, n)
-        out[name] = {"ms_per_step": ms, "env_steps_per_s": m / (ms * 1e-3)}
+        ms = timed(env, n, graph_steps)
+        out[name] = {"us_per_step": ms * 1e3, "env_steps_per_s": m / (ms * 1e-3)}
         del env
         torch.cuda.empty_cache()
     return out

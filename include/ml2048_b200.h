@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ML2048_ABI_VERSION 4
+#define ML2048_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define ML2048_API __attribute__((visibility("default")))
@@ -57,8 +57,12 @@ enum { ML2048_ACT_U8 = 0, ML2048_ACT_I32 = 1, ML2048_ACT_I64 = 2 };
 /* where actions come from */
 enum {
     ML2048_ACTIONS_GIVEN = 0,       /* read `actions` */
-    ML2048_ACTIONS_RANDOM_VALID = 1 /* uniform over valid actions, Philox (policy/random.py:17-27);
-                                       the chosen action is written to `actions_out` when not null */
+    ML2048_ACTIONS_RANDOM_VALID = 1, /* uniform over valid actions, Philox (policy/random.py:17-27);
+                                        the chosen action is written to `actions_out` when not null */
+    ML2048_ACTIONS_FROM_LOGITS = 2   /* masked categorical sample from the policy head's logits
+                                        (_sample_action, policy/actor_critic.py:56-76): invalid actions get
+                                        finfo.min, softmax, one Philox uniform picks the action; the action goes to
+                                        `actions_out`, its log-probability to `log_prob_out` (when not null) */
 };
 
 /* fused observation encoding (policy/_network.py:86-95): out[g][k][c] = (board[g][c] == k), k < 16 */
@@ -148,6 +152,22 @@ typedef struct {
     int32_t *episode_steps;        /* [episode_capacity] */
     float *episode_score;          /* [episode_capacity] */
     uint8_t *episode_max_tile;     /* [episode_capacity]; 0 = not finished yet */
+
+    /* ML2048_ACTIONS_FROM_LOGITS */
+    const float *logits;           /* [num_games][4] f32, 16-byte aligned */
+    float *log_prob_out;           /* [num_games] or null */
+
+    /* Transition record (each pointer nullable): one row of the caller's (use, step, game) rollout buffers with
+     * the REPLAY_SPEC dtypes (replay.py:10-20), written by the kernel instead of the seven host copies of
+     * Trainer.on_stepped (run_train3.py:138-149).  Stale fields of invalid moves are copied stale, as there. */
+    int8_t *tr_state;              /* [num_games][16] = prev_state */
+    uint8_t *tr_valid_actions;     /* [num_games][4]  = prev_valid_actions (bool bytes) */
+    int8_t *tr_action;             /* [num_games] */
+    float *tr_reward;              /* [num_games] */
+    int8_t *tr_next_state;         /* [num_games][16] */
+    uint8_t *tr_next_valid_actions;/* [num_games][4] */
+    int32_t *tr_step;              /* [num_games] */
+    uint8_t *tr_terminated;        /* [num_games] (bool bytes) */
 } ml2048_step_args;
 
 /* Arguments of the auto-reset.  Replaces the host loop of VecGame.prepare (game_numba.py:629-658):
@@ -229,6 +249,18 @@ ML2048_API int ml2048_max_tile_hist(const void *board, const uint8_t *terminated
 /* uniform-over-valid action sampler (policy/random.py:17-27) as a stand-alone op */
 ML2048_API int ml2048_sample_random_valid(const void *valid, uint8_t *actions_out, int64_t num_games, int64_t slot_base,
                                uint64_t philox_seed, uint64_t philox_counter, void *stream);
+
+/* _sample_action (policy/actor_critic.py:56-76) as a stand-alone op: masked categorical sample + log-probability.
+ * valid: [num_games][4] bool/u8; actions_u8 / actions_i64: either may be null; log_prob: [num_games] or null */
+ML2048_API int ml2048_sample_masked_categorical(const float *logits, const void *valid, uint8_t *actions_u8, int64_t *actions_i64,
+                                                float *log_prob, int64_t num_games, int64_t slot_base, uint64_t philox_seed,
+                                                uint64_t philox_counter, void *stream);
+
+/* compute_gae's recurrence (gae.py:50, :65-68) over (use, step, game) f32 tensors, one thread per (use, game):
+ *   delta = gamma * v1 * (1 - terminated) + reward - v0;  tmp = delta[t] + (tmp * gamma*lambda) * (1 - terminated[t]), t descending
+ * rounded exactly like the reference's torch fp32 ops (no fused multiply-add). */
+ML2048_API int ml2048_gae(const float *v0, const float *v1, const float *reward, const uint8_t *terminated, float *adv,
+                          int64_t use_count, int64_t step_count, int64_t game_count, float gamma, float coef, void *stream);
 
 /* host helpers (no GPU work) */
 ML2048_API uint32_t ml2048_two_mask(const float *host_randfloat16, double two_prob);   /* game_numba.py:207 (f32 -> f64 compare) */

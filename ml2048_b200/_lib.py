@@ -12,14 +12,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libml2048_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 STATS_REPLICAS = 64
 STATS_WORDS = 24  # 20 histogram bins + episodes, score_sum, step_sum, score_max (unsigned long long each)
 
 REWARD_NORMAL, REWARD_IMPROVED, REWARD_RANK, REWARD_MAXCELL = 0, 1, 2, 3
 RNG_REPLAY, RNG_PHILOX = 0, 1
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
-ACTIONS_GIVEN, ACTIONS_RANDOM_VALID = 0, 1
+ACTIONS_GIVEN, ACTIONS_RANDOM_VALID, ACTIONS_FROM_LOGITS = 0, 1, 2
 ONEHOT_NONE, ONEHOT_F32, ONEHOT_BF16, ONEHOT_U8 = 0, 1, 2, 3
 
 ERRORS = {-1: "null pointer", -2: "misaligned pointer", -3: "bad size", -4: "bad enum", -5: "struct size mismatch"}
@@ -67,6 +67,16 @@ class StepArgs(C.Structure):
         ("episode_steps", C.c_void_p),
         ("episode_score", C.c_void_p),
         ("episode_max_tile", C.c_void_p),
+        ("logits", C.c_void_p),
+        ("log_prob_out", C.c_void_p),
+        ("tr_state", C.c_void_p),
+        ("tr_valid_actions", C.c_void_p),
+        ("tr_action", C.c_void_p),
+        ("tr_reward", C.c_void_p),
+        ("tr_next_state", C.c_void_p),
+        ("tr_next_valid_actions", C.c_void_p),
+        ("tr_step", C.c_void_p),
+        ("tr_terminated", C.c_void_p),
     ]
 
 
@@ -121,6 +131,8 @@ SYMBOLS = {
     "ml2048_valid_actions": (C.c_int, [_VP, _VP, _I64, _VP]),
     "ml2048_max_tile_hist": (C.c_int, [_VP, _VP, _I64, _VP, _VP]),
     "ml2048_sample_random_valid": (C.c_int, [_VP, _VP, _I64, _I64, _U64, _U64, _VP]),
+    "ml2048_sample_masked_categorical": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _U64, _U64, _VP]),
+    "ml2048_gae": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _I64, C.c_float, C.c_float, _VP]),
     "ml2048_two_mask": (_U32, [_VP, C.c_double]),
     "ml2048_two_threshold": (_U32, [C.c_double]),
     "ml2048_pack_randperm_keys": (C.c_int, [_VP, _VP, _I64]),

@@ -310,4 +310,33 @@ ML2048_FN u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
     return u32x4{c0, c1, c2, c3};
 }
 
+// Masked categorical sample (policy/actor_critic.py:56-76): invalid actions get finfo.min, the logits are
+// normalised as torch's Categorical does (x - logsumexp(x), logsumexp = max + log(sum(exp(x - max)))), one
+// uniform u in [0,1) picks the action by inverse CDF.  `mask_bits` bit k = action k valid.  Returns the action
+// and its log-probability.  (Device only: uses expf/logf.)
+#if defined(__CUDACC__)
+ML2048_FN uint32_t sample_masked_categorical(float l0, float l1, float l2, float l3, uint32_t mask_bits, uint32_t rnd,
+                                             float &log_prob)
+{
+    const float kMin = -3.4028234663852886e38f;  // torch.finfo(float32).min
+    l0 = (mask_bits & 1u) ? l0 : kMin;
+    l1 = (mask_bits & 2u) ? l1 : kMin;
+    l2 = (mask_bits & 4u) ? l2 : kMin;
+    l3 = (mask_bits & 8u) ? l3 : kMin;
+    const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx), e3 = expf(l3 - mx);
+    const float total = ((e0 + e1) + e2) + e3;
+    const float lse = logf(total) + mx;
+    const float t = (float)(rnd >> 8) * (1.0f / 16777216.0f) * total;
+    const float c0 = e0, c1 = c0 + e1, c2 = c1 + e2;
+    uint32_t action = (t < c0) ? 0u : (t < c1) ? 1u : (t < c2) ? 2u : 3u;
+    // rounding may push t onto an impossible action (e == 0): fall back to the last possible one
+    const float ea = action == 0u ? e0 : action == 1u ? e1 : action == 2u ? e2 : e3;
+    if (ea == 0.0f) action = (e3 > 0.0f) ? 3u : (e2 > 0.0f) ? 2u : (e1 > 0.0f) ? 1u : 0u;
+    const float la = action == 0u ? l0 : action == 1u ? l1 : action == 2u ? l2 : l3;
+    log_prob = la - lse;
+    return action;
+}
+#endif
+
 }  // namespace ml2048

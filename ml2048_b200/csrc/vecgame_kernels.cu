@@ -131,7 +131,9 @@ __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, 
 }
 
 // Replaces _vec_step (game_numba.py:701-738) + the prev copies of VecGame.step (:672-673).
-template <int kRng, bool kLog, int kOneHot>
+// kFull adds the rollout extras (policy-logits sampling, transition record, episode log); the lean variant
+// compiles them out so the plain step pays nothing for them.
+template <int kRng, bool kLog, int kOneHot, bool kFull>
 __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_args a)
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kStepThreads : 1];
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_ar
         const uint4 bd = reinterpret_cast<const uint4 *>(a.board_in)[g];
         const uint64_t slot = (uint64_t)(a.slot_base + g);
         u32x4 rnd = {0u, 0u, 0u, 0u};
-        if (kRng == ML2048_RNG_PHILOX || a.action_mode == ML2048_ACTIONS_RANDOM_VALID)
+        if (kRng == ML2048_RNG_PHILOX || a.action_mode != ML2048_ACTIONS_GIVEN)
             rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)philox_counter,
                                 (uint32_t)(philox_counter >> 32), (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
         uint32_t action;
@@ -170,12 +172,23 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_ar
             const uint32_t nv = popc32(bits);
             action = nv ? kth_set_bit16(bits, umulhi32(rnd.z, nv)) : 0u;
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
+        } else if (kFull && a.action_mode == ML2048_ACTIONS_FROM_LOGITS) {
+            const uint32_t vm = reinterpret_cast<const uint32_t *>(a.valid_in)[g];
+            const uint32_t bits = (vm & 1u) | ((vm >> 7) & 2u) | ((vm >> 14) & 4u) | ((vm >> 21) & 8u);
+            const float4 lg = reinterpret_cast<const float4 *>(a.logits)[g];
+            float lp;
+            action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.z, lp);
+            if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
+            if (a.log_prob_out) a.log_prob_out[g] = lp;
         } else {
             action = load_action(a.actions, a.action_dtype, g);
         }
 
         uint32_t r0 = bd.x, r1 = bd.y, r2 = bd.z, r3 = bd.w;
         Fusions f;
+        float tr_reward = 0.0f;
+        int32_t tr_step = 0;
+        uint32_t tr_term = 0u, tr_mask = 0u;
         move_board(r0, r1, r2, r3, action & 3u, f);
         // valid_actions[action] (game_numba.py:718) == "the move changes the board"; out-of-range
         // actions (which the reference would index out of bounds with) count as invalid moves
@@ -230,7 +243,8 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_ar
                 fusion_log(f, m0, m1, m2, m3);
                 reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(m0, m1, m2, m3);
             }
-            if (dead && a.episode_max_tile) {
+            tr_reward = reward, tr_step = nstep, tr_term = dead ? 1 : 0, tr_mask = vm;
+            if (kFull && dead && a.episode_max_tile) {
                 // eval_perf.py semantics: episodes are keyed by game id, not by finishing order
                 const int64_t e = (int64_t)a.id[g] - a.episode_id_base;
                 if (e >= 0 && e < a.episode_capacity) {
@@ -252,11 +266,28 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const ml2048_step_ar
         } else {
             // invalid move: only `invalid` changes (game_numba.py:737-738); the board is carried over
             r0 = bd.x, r1 = bd.y, r2 = bd.z, r3 = bd.w;
-            reinterpret_cast<uint32_t *>(a.valid_out)[g] = valid_mask(r0, r1, r2, r3);
+            tr_mask = valid_mask(r0, r1, r2, r3);
+            reinterpret_cast<uint32_t *>(a.valid_out)[g] = tr_mask;
             a.invalid[g] = 1;
+            if (kFull) {  // stale values are recorded stale (run_train3.py:146-148)
+                if (a.tr_reward) tr_reward = a.reward[g];
+                if (a.tr_step) tr_step = a.step[g];
+                if (a.tr_terminated) tr_term = a.terminated[g];
+            }
         }
         out_board = make_uint4(r0, r1, r2, r3);
         reinterpret_cast<uint4 *>(a.board_out)[g] = out_board;
+        if (kFull) {  // transition record (REPLAY_SPEC row, replay.py:10-20)
+            if (a.tr_state) reinterpret_cast<uint4 *>(a.tr_state)[g] = bd;
+            if (a.tr_valid_actions)
+                reinterpret_cast<uint32_t *>(a.tr_valid_actions)[g] = reinterpret_cast<const uint32_t *>(a.valid_in)[g];
+            if (a.tr_action) a.tr_action[g] = (int8_t)action;
+            if (a.tr_reward) a.tr_reward[g] = tr_reward;
+            if (a.tr_next_state) reinterpret_cast<uint4 *>(a.tr_next_state)[g] = out_board;
+            if (a.tr_next_valid_actions) reinterpret_cast<uint32_t *>(a.tr_next_valid_actions)[g] = tr_mask;
+            if (a.tr_step) a.tr_step[g] = tr_step;
+            if (a.tr_terminated) a.tr_terminated[g] = (uint8_t)tr_term;
+        }
     }
 
     if (kOneHot != ML2048_ONEHOT_NONE) {
@@ -471,6 +502,47 @@ __global__ void __launch_bounds__(kStepThreads) sample_random_valid_kernel(const
     actions[g] = (uint8_t)(nv ? kth_set_bit16(bits, umulhi32(rnd.z, nv)) : 0u);
 }
 
+__global__ void __launch_bounds__(kStepThreads) sample_categorical_kernel(const float4 *logits, const uint32_t *valid, uint8_t *act8,
+                                                                          long long *act64, float *log_prob, int64_t num_games,
+                                                                          int64_t slot_base, uint64_t seed, uint64_t counter)
+{
+    const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+    if (g >= num_games) return;
+    const uint64_t slot = (uint64_t)(slot_base + g);
+    const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)counter, (uint32_t)(counter >> 32),
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t vm = valid[g];
+    const uint32_t bits = ((vm & 0xffu) ? 1u : 0u) | ((vm & 0xff00u) ? 2u : 0u) | ((vm & 0xff0000u) ? 4u : 0u) | ((vm & 0xff000000u) ? 8u : 0u);
+    const float4 lg = logits[g];
+    float lp;
+    const uint32_t action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.z, lp);
+    if (act8) act8[g] = (uint8_t)action;
+    if (act64) act64[g] = (long long)action;
+    if (log_prob) log_prob[g] = lp;
+}
+
+// compute_gae's reverse scan (gae.py:50, :65-68).  Layout (use, step, game), game fastest: a warp reads 32
+// adjacent games of one (use, step) row.  __fmul_rn/__fadd_rn keep the reference's rounding (no FMA contraction).
+__global__ void __launch_bounds__(kStepThreads) gae_kernel(const float *v0, const float *v1, const float *reward,
+                                                           const uint8_t *terminated, float *adv, int64_t step_count,
+                                                           int64_t game_count, int64_t total, float gamma, float coef)
+{
+    const int64_t i = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;  // over use x game
+    if (i >= total) return;
+    const int64_t u = i / game_count, g = i - u * game_count;
+    const int64_t base = u * step_count * game_count + g;
+    float tmp = 0.0f;
+    for (int64_t t = step_count - 1; t >= 0; --t) {
+        const int64_t k = base + t * game_count;
+        const float mask = terminated[k] ? 0.0f : 1.0f;
+        // delta = gamma * v1 * mask + reward - v0, evaluated left to right in fp32
+        const float delta = __fsub_rn(__fadd_rn(__fmul_rn(__fmul_rn(gamma, v1[k]), mask), reward[k]), v0[k]);
+        tmp = __fmul_rn(tmp, coef);
+        tmp = __fadd_rn(delta, __fmul_rn(tmp, mask));
+        adv[k] = tmp;
+    }
+}
+
 __global__ void fill_terminated_kernel(uint8_t *terminated, int64_t num_games, int64_t padded)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -487,18 +559,27 @@ inline int launch_status()
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-template <int kRng, bool kLog>
+template <int kRng, bool kLog, bool kFull>
 int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
 {
     const unsigned grid = (unsigned)((a.num_games + kStepThreads - 1) / kStepThreads);
     switch (a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE) {
-    case ML2048_ONEHOT_NONE: step_kernel<kRng, kLog, ML2048_ONEHOT_NONE><<<grid, kStepThreads, 0, s>>>(a); break;
-    case ML2048_ONEHOT_F32: step_kernel<kRng, kLog, ML2048_ONEHOT_F32><<<grid, kStepThreads, 0, s>>>(a); break;
-    case ML2048_ONEHOT_BF16: step_kernel<kRng, kLog, ML2048_ONEHOT_BF16><<<grid, kStepThreads, 0, s>>>(a); break;
-    case ML2048_ONEHOT_U8: step_kernel<kRng, kLog, ML2048_ONEHOT_U8><<<grid, kStepThreads, 0, s>>>(a); break;
+    case ML2048_ONEHOT_NONE: step_kernel<kRng, kLog, ML2048_ONEHOT_NONE, kFull><<<grid, kStepThreads, 0, s>>>(a); break;
+    case ML2048_ONEHOT_F32: step_kernel<kRng, kLog, ML2048_ONEHOT_F32, kFull><<<grid, kStepThreads, 0, s>>>(a); break;
+    case ML2048_ONEHOT_BF16: step_kernel<kRng, kLog, ML2048_ONEHOT_BF16, kFull><<<grid, kStepThreads, 0, s>>>(a); break;
+    case ML2048_ONEHOT_U8: step_kernel<kRng, kLog, ML2048_ONEHOT_U8, kFull><<<grid, kStepThreads, 0, s>>>(a); break;
     default: return ML2048_E_ENUM;
     }
     return launch_status();
+}
+
+template <int kRng>
+int launch_step(const ml2048_step_args &a, cudaStream_t s)
+{
+    const bool full = a.action_mode == ML2048_ACTIONS_FROM_LOGITS || a.episode_max_tile || a.tr_state || a.tr_valid_actions ||
+                      a.tr_action || a.tr_reward || a.tr_next_state || a.tr_next_valid_actions || a.tr_step || a.tr_terminated;
+    if (full) return a.merged ? launch_step_onehot<kRng, true, true>(a, s) : launch_step_onehot<kRng, false, true>(a, s);
+    return a.merged ? launch_step_onehot<kRng, true, false>(a, s) : launch_step_onehot<kRng, false, false>(a, s);
 }
 
 }  // namespace
@@ -536,9 +617,16 @@ int ml2048_step(const ml2048_step_args *args, void *stream)
             return ML2048_E_ALIGN;
     } else if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
         if (!a.valid_in) return ML2048_E_NULL;
+    } else if (a.action_mode == ML2048_ACTIONS_FROM_LOGITS) {
+        if (!a.valid_in || !a.logits) return ML2048_E_NULL;
+        if (misaligned(a.logits, 16) || misaligned(a.log_prob_out, 4)) return ML2048_E_ALIGN;
     } else {
         return ML2048_E_ENUM;
     }
+    if (a.tr_valid_actions && !a.valid_in) return ML2048_E_NULL;
+    if (misaligned(a.tr_state, 16) || misaligned(a.tr_next_state, 16) || misaligned(a.tr_valid_actions, 4) ||
+        misaligned(a.tr_next_valid_actions, 4) || misaligned(a.tr_reward, 4) || misaligned(a.tr_step, 4))
+        return ML2048_E_ALIGN;
     if (a.onehot_out && (a.onehot_dtype < ML2048_ONEHOT_F32 || a.onehot_dtype > ML2048_ONEHOT_U8)) return ML2048_E_ENUM;
     if (a.episode_max_tile && (!a.id || !a.episode_steps || !a.episode_score || a.episode_capacity <= 0)) return ML2048_E_NULL;
     if (a.sched) {
@@ -550,10 +638,9 @@ int ml2048_step(const ml2048_step_args *args, void *stream)
     if (a.rng_mode == ML2048_RNG_REPLAY) {
         if (!a.randperm_keys) return ML2048_E_NULL;
         if (misaligned(a.randperm_keys, 16)) return ML2048_E_ALIGN;
-        return a.merged ? launch_step_onehot<ML2048_RNG_REPLAY, true>(a, s) : launch_step_onehot<ML2048_RNG_REPLAY, false>(a, s);
+        return launch_step<ML2048_RNG_REPLAY>(a, s);
     }
-    if (a.rng_mode == ML2048_RNG_PHILOX)
-        return a.merged ? launch_step_onehot<ML2048_RNG_PHILOX, true>(a, s) : launch_step_onehot<ML2048_RNG_PHILOX, false>(a, s);
+    if (a.rng_mode == ML2048_RNG_PHILOX) return launch_step<ML2048_RNG_PHILOX>(a, s);
     return ML2048_E_ENUM;
 }
 
@@ -692,6 +779,32 @@ int ml2048_sample_random_valid(const void *valid, uint8_t *actions_out, int64_t 
     const unsigned grid = (unsigned)((num_games + kStepThreads - 1) / kStepThreads);
     sample_random_valid_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const uint32_t *>(valid), actions_out, num_games, slot_base, philox_seed, philox_counter);
+    return launch_status();
+}
+
+int ml2048_sample_masked_categorical(const float *logits, const void *valid, uint8_t *actions_u8, int64_t *actions_i64, float *log_prob,
+                                     int64_t num_games, int64_t slot_base, uint64_t philox_seed, uint64_t philox_counter, void *stream)
+{
+    if (num_games <= 0) return ML2048_E_SIZE;
+    if (!logits || !valid || (!actions_u8 && !actions_i64)) return ML2048_E_NULL;
+    if (misaligned(logits, 16) || misaligned(valid, 4) || misaligned(actions_i64, 8) || misaligned(log_prob, 4)) return ML2048_E_ALIGN;
+    const unsigned grid = (unsigned)((num_games + kStepThreads - 1) / kStepThreads);
+    sample_categorical_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4 *>(logits), reinterpret_cast<const uint32_t *>(valid), actions_u8,
+        reinterpret_cast<long long *>(actions_i64), log_prob, num_games, slot_base, philox_seed, philox_counter);
+    return launch_status();
+}
+
+int ml2048_gae(const float *v0, const float *v1, const float *reward, const uint8_t *terminated, float *adv, int64_t use_count,
+               int64_t step_count, int64_t game_count, float gamma, float coef, void *stream)
+{
+    if (use_count <= 0 || step_count <= 0 || game_count <= 0) return ML2048_E_SIZE;
+    if (!v0 || !v1 || !reward || !terminated || !adv) return ML2048_E_NULL;
+    if (misaligned(v0, 4) || misaligned(v1, 4) || misaligned(reward, 4) || misaligned(adv, 4)) return ML2048_E_ALIGN;
+    const int64_t total = use_count * game_count;
+    const unsigned grid = (unsigned)((total + kStepThreads - 1) / kStepThreads);
+    gae_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(v0, v1, reward, terminated, adv, step_count, game_count,
+                                                                            total, gamma, coef);
     return launch_status();
 }
 

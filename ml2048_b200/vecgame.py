@@ -240,6 +240,8 @@ class VecGame:
         self._randperm = np.empty((RAND_ROWS, 16), dtype=np.uint8)
         self._randfloat = np.empty((RAND_ROWS,), dtype=np.float32)
         self._tables_host = np.zeros((2, RAND_ROWS, 16), dtype=np.uint8)  # staging: randperm + its inverse-form keys
+        self._record_active = False
+        self._keep_record = None
         self._sched_len = 0   # entries of the device-resident schedule (0 = eager mode: host draws per call)
         self._sched_pos = 0   # entries consumed so far (host mirror of the device cursor)
         self._rand_step = 0
@@ -533,23 +535,88 @@ class VecGame:
             return coin
         return self._schedule.refresh_coin()
 
-    def step(self, actions, *, fetch: Optional[tuple] = None) -> VecStepResult:
+    def step(self, actions, *, fetch: Optional[tuple] = None, record: Optional[dict] = None) -> VecStepResult:
         """game_numba.py:660-698.  ``actions``: (M,) integers in 0..3 (NumPy array, CPU or CUDA tensor).
+
+        ``record``: dict of CUDA tensors (one row of the caller's (use, step, game) rollout buffers, REPLAY_SPEC
+        names and dtypes, replay.py:10-20) that the kernel fills with this transition -- what
+        ``Trainer.on_stepped`` copies from the host in the reference (run_train3.py:138-149).
 
         ``fetch`` (NumPy mode, host actions): result keys the caller is going to read.  For large batches the
         step then runs as a pipeline over slices of the games -- actions H2D, kernel, results D2H on three
         streams -- so the PCIe copies in both directions overlap the kernel instead of following it."""
         assert tuple(actions.shape) == (self._size,), actions.shape  # game_numba.py:668
-        if fetch and self._can_pipeline(actions):
+        if fetch and not record and self._can_pipeline(actions):
             return self._step_pipelined(actions, tuple(fetch))
         a = self._step_args
         dev_actions, a.action_dtype = self._stage_actions(actions)
         a.action_mode = _lib.ACTIONS_GIVEN
         a.actions = dev_actions.data_ptr()
         a.actions_out = None
+        self._set_record(record)
         self._launch_step()
         self._keepalive = dev_actions
         return VecStepResult(self)
+
+    def step_from_logits(self, logits: torch.Tensor, *, log_prob_out: Optional[torch.Tensor] = None,
+                         record: Optional[dict] = None) -> VecStepResult:
+        """One step whose actions are SAMPLED INSIDE THE KERNEL from the policy head's logits (M,4) f32, masked by
+        the current valid actions exactly like ``_sample_action`` (policy/actor_critic.py:56-76).  The sampled
+        actions land in ``sampled_actions`` (uint8), their log-probabilities in ``log_prob_out`` (f32 (M,))."""
+        if not (isinstance(logits, torch.Tensor) and logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
+                and tuple(logits.shape) == (self._size, 4)):
+            raise ValueError(f"logits must be a contiguous CUDA float32 ({self._size},4) tensor")
+        if log_prob_out is not None and not (log_prob_out.is_cuda and log_prob_out.dtype == torch.float32
+                                             and log_prob_out.is_contiguous() and log_prob_out.numel() == self._size):
+            raise ValueError("log_prob_out must be a contiguous CUDA float32 (M,) tensor")
+        a = self._step_args
+        a.action_mode = _lib.ACTIONS_FROM_LOGITS
+        a.action_dtype = _lib.ACT_U8
+        a.actions = None
+        a.actions_out = self._p(self._actions_out)
+        a.logits = logits.data_ptr()
+        a.log_prob_out = self._p(log_prob_out)
+        self._set_record(record)
+        self._launch_step()
+        a.logits = None
+        a.log_prob_out = None
+        self._keepalive = (logits, log_prob_out)
+        return VecStepResult(self)
+
+    @property
+    def sampled_actions(self) -> torch.Tensor:
+        """uint8 (M,): the actions the kernel chose in the last step_random(return_actions=True) / step_from_logits()."""
+        return self._actions_out
+
+    _RECORD_SPEC = {  # REPLAY_SPEC rows (replay.py:10-20) the step kernel can fill: name -> (trailing shape, dtypes)
+        "state": ((16,), (torch.int8, torch.uint8)),
+        "valid_actions": ((4,), (torch.bool, torch.uint8)),
+        "action": ((), (torch.int8, torch.uint8)),
+        "reward": ((), (torch.float32,)),
+        "next_state": ((16,), (torch.int8, torch.uint8)),
+        "next_valid_actions": ((4,), (torch.bool, torch.uint8)),
+        "step": ((), (torch.int32,)),
+        "terminated": ((), (torch.bool, torch.uint8)),
+    }
+
+    def _set_record(self, record: Optional[dict]) -> None:
+        """Point the kernel's transition outputs at the caller's buffer rows (or clear them)."""
+        a = self._step_args
+        if not record and not self._record_active:
+            return
+        for name, (shape, dtypes) in self._RECORD_SPEC.items():
+            t = record.get(name) if record else None
+            if t is not None:
+                if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous() and t.dtype in dtypes
+                        and tuple(t.shape) == (self._size,) + shape):
+                    raise ValueError(f"record[{name!r}] must be a contiguous CUDA tensor {(self._size,) + shape} of {dtypes}")
+            setattr(a, "tr_" + name, None if t is None else t.data_ptr())
+        if record:
+            unknown = set(record) - set(self._RECORD_SPEC)
+            if unknown:
+                raise KeyError(f"unknown record fields {sorted(unknown)}")
+        self._record_active = bool(record)
+        self._keep_record = record
 
     def summary(self) -> list[Any]:
         """game_numba.py:593-604: (tile value, count, share) of the max tile over all live boards."""
@@ -587,7 +654,7 @@ class VecGame:
     # extras: device-side policy for synthetic rollouts, statistics, sharding
     # ------------------------------------------------------------------------------------------
 
-    def step_random(self, *, return_actions: bool = False):
+    def step_random(self, *, return_actions: bool = False, record: Optional[dict] = None):
         """One step with uniformly random VALID actions chosen inside the kernel (Philox) --
         the benchmark policy (semantics of policy/random.py:17-27), no action array crosses the bus."""
         a = self._step_args
@@ -595,6 +662,7 @@ class VecGame:
         a.action_dtype = _lib.ACT_U8
         a.actions = None
         a.actions_out = self._p(self._actions_out) if return_actions else None
+        self._set_record(record)
         self._launch_step()
         return VecStepResult(self)
 

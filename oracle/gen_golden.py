@@ -15,6 +15,7 @@ What is produced (all from the reference's own functions, reference: src/ml2048/
   boards.npz           random boards x 4 actions: moved board, merged, mask, the four rewards
   rollout_*.npz        lock-step rollouts through VecGame (prepare/observations/step), every
                        VecStepResult field + ids + reset indices (full or CRC32 digests)
+  gae.npz              compute_gae (gae.py:7-68) on random fp32 inputs with a stand-in critic
   schedule_*.npz       the host random draws of one rollout recorded from the reference's generator
                        (tables at every refresh, coins, offsets): input of the "replay" mode
 """
@@ -208,12 +209,46 @@ def gen_schedules() -> None:
         print(f"schedule {name}: refreshes={len(proxy.perms)}")
 
 
+def gen_gae() -> None:
+    """compute_gae (gae.py:7-68) of the live reference on random fp32 inputs, with a stand-in critic that returns
+    pre-drawn values (first call: v0, second call: v1)."""
+    import torch
+    from ml2048.gae import compute_gae
+    from ml2048.stats import TensorStats
+
+    torch.manual_seed(0)
+    out = {}
+    for tag, (u, s_, g), gamma, lam in (("a", (2, 16, 257), 0.997, 0.95), ("b", (1, 64, 33), 0.9, 0.5), ("c", (3, 5, 1024), 1.0, 1.0)):
+        v0 = torch.randn(u, s_, g) * 50
+        v1 = torch.randn(u, s_, g) * 50
+        reward = (torch.randint(0, 64, (u, s_, g)) * 4).float()
+        terminated = torch.rand(u, s_, g) < 0.05
+
+        class Critic:
+            def __init__(self):
+                self.calls = 0
+
+            def eval_value(self, state, valid):
+                self.calls += 1
+                return v0 if self.calls == 1 else v1
+
+        data = {"state": torch.zeros(u, s_, g, 16, dtype=torch.int8), "valid_actions": torch.ones(u, s_, g, 4, dtype=torch.bool),
+                "reward": reward, "next_state": torch.zeros(u, s_, g, 16, dtype=torch.int8),
+                "next_valid_actions": torch.ones(u, s_, g, 4, dtype=torch.bool), "terminated": terminated,
+                "adv": torch.zeros(u, s_, g)}
+        compute_gae(Critic(), data, gamma=gamma, lambda_=lam, tensor_stats=TensorStats())
+        for k, v in (("v0", v0), ("v1", v1), ("reward", reward), ("terminated", terminated), ("adv", data["adv"])):
+            out[f"{tag}_{k}"] = v.numpy()
+        out[f"{tag}_params"] = np.array([gamma, lam], np.float64)
+    np.savez_compressed(os.path.join(OUT_DIR, "gae.npz"), **out)
+
+
 def main() -> None:
     os.makedirs(OUT_DIR, exist_ok=True)
     print("numba", numba.__version__, "numpy", np.__version__)
     only = set(sys.argv[1:])
     for name, fn in (("kat", gen_kat), ("lines", gen_line_table), ("boards", gen_boards), ("rollouts", gen_rollouts),
-                     ("schedules", gen_schedules)):
+                     ("schedules", gen_schedules), ("gae", gen_gae)):
         if not only or name in only:
             fn()
     with open(os.path.join(OUT_DIR, "PROVENANCE.txt"), "w") as fh:
