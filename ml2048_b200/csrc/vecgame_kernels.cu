@@ -532,10 +532,27 @@ __global__ void __launch_bounds__(kStepThreads) gae_kernel(const float *v0, cons
     const int64_t u = i / game_count, g = i - u * game_count;
     const int64_t base = u * step_count * game_count + g;
     float tmp = 0.0f;
-    for (int64_t t = step_count - 1; t >= 0; --t) {
+    // the loads do not depend on the running value: fetch four steps at a time so that several rows are in flight
+    int64_t t = step_count - 1;
+    for (; t >= 3; t -= 4) {
+        float a0[4], a1[4], rw[4], mk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t k = base + (t - j) * game_count;
+            a0[j] = v0[k], a1[j] = v1[k], rw[j] = reward[k], mk[j] = terminated[k] ? 0.0f : 1.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // delta = gamma * v1 * mask + reward - v0, evaluated left to right in fp32
+            const float delta = __fsub_rn(__fadd_rn(__fmul_rn(__fmul_rn(gamma, a1[j]), mk[j]), rw[j]), a0[j]);
+            tmp = __fmul_rn(tmp, coef);
+            tmp = __fadd_rn(delta, __fmul_rn(tmp, mk[j]));
+            adv[base + (t - j) * game_count] = tmp;
+        }
+    }
+    for (; t >= 0; --t) {
         const int64_t k = base + t * game_count;
         const float mask = terminated[k] ? 0.0f : 1.0f;
-        // delta = gamma * v1 * mask + reward - v0, evaluated left to right in fp32
         const float delta = __fsub_rn(__fadd_rn(__fmul_rn(__fmul_rn(gamma, v1[k]), mask), reward[k]), v0[k]);
         tmp = __fmul_rn(tmp, coef);
         tmp = __fadd_rn(delta, __fmul_rn(tmp, mask));
