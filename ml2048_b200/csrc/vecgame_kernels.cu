@@ -103,21 +103,23 @@ __device__ __forceinline__ void write_onehot_tile(const uint4 *sboards, int game
         store_streaming(out + (int64_t)g * kPer + piece, P::make(sboards, g, piece));
 }
 
-// One game's one-hot row written by a single thread (reset path: rare, so no cooperation needed).
+// One game's one-hot row written by a whole warp (reset path): lane l stores pieces l, l+32, ... so that one warp
+// instruction covers up to 512 contiguous bytes.
 template <int kDtype>
-__device__ __forceinline__ void write_onehot_single(uint4 board, void *out_base, int64_t game)
+__device__ __forceinline__ void write_onehot_warp(uint4 board, void *out_base, int64_t game, int lane)
 {
     using P = OneHotPiece<kDtype>;
     typename P::vec *out = reinterpret_cast<typename P::vec *>(out_base) + game * P::kPiecesPerGame;
-    for (int piece = 0; piece < P::kPiecesPerGame; ++piece)
-        out[piece] = P::make(&board, 0, piece);
+#pragma unroll
+    for (int piece = lane; piece < P::kPiecesPerGame; piece += 32)
+        store_streaming(out + piece, P::make(&board, 0, piece));
 }
 
-__device__ __forceinline__ void write_onehot_single_dyn(int dtype, uint4 board, void *out_base, int64_t game)
+__device__ __forceinline__ void write_onehot_warp_dyn(int dtype, uint4 board, void *out_base, int64_t game, int lane)
 {
-    if (dtype == ML2048_ONEHOT_F32) write_onehot_single<ML2048_ONEHOT_F32>(board, out_base, game);
-    else if (dtype == ML2048_ONEHOT_BF16) write_onehot_single<ML2048_ONEHOT_BF16>(board, out_base, game);
-    else if (dtype == ML2048_ONEHOT_U8) write_onehot_single<ML2048_ONEHOT_U8>(board, out_base, game);
+    if (dtype == ML2048_ONEHOT_F32) write_onehot_warp<ML2048_ONEHOT_F32>(board, out_base, game, lane);
+    else if (dtype == ML2048_ONEHOT_BF16) write_onehot_warp<ML2048_ONEHOT_BF16>(board, out_base, game, lane);
+    else if (dtype == ML2048_ONEHOT_U8) write_onehot_warp<ML2048_ONEHOT_U8>(board, out_base, game, lane);
 }
 
 // ---- the step kernel ------------------------------------------------------------------------
@@ -389,7 +391,8 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
     __syncthreads();
     int wbase = 0;
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += warp_tot[w];
-    if (mask == 0u) return;
+    const bool had_any = mask != 0u;
+    const int lane = threadIdx.x & 31;
 
     int64_t rand_base = a.rand_base;
     uint32_t two_mask = a.two_mask;
@@ -404,12 +407,17 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
     }
     int64_t order = (int64_t)tile_offsets[blockIdx.x] + wbase + inc - mine;  // rank among all reset slots
     const int64_t id_base = *id_base_slot + (a.id_offset ? *a.id_offset : 0);
-    uint4 clear16 = reinterpret_cast<const uint4 *>(a.terminated)[i];
 
-    while (mask) {
+    // rounds: in each one every lane that still has a finished game resets one; the one-hot rows of the round
+    // are then written by the whole warp, one game after the other
+    while (__any_sync(0xffffffffu, mask != 0u)) {
+        const bool has = mask != 0u;
+        uint4 bd = make_uint4(0u, 0u, 0u, 0u);
+        long long g = 0;
+        if (has) {
         const int j = __ffs((int)mask) - 1;
         mask &= mask - 1u;
-        const int64_t g = i * 16 + j;
+        g = i * 16 + j;
         const uint64_t slot = (uint64_t)(a.slot_base + g);
         uint32_t c0, c1, v0, v1;
         if (kRng == ML2048_RNG_REPLAY) {
@@ -433,7 +441,7 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
         uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u;
         put_cell(r0, r1, r2, r3, c0 & 15u, v0);
         put_cell(r0, r1, r2, r3, c1 & 15u, v1);
-        const uint4 bd = make_uint4(r0, r1, r2, r3);
+        bd = make_uint4(r0, r1, r2, r3);
         reinterpret_cast<uint4 *>(a.board)[g] = bd;
         reinterpret_cast<uint32_t *>(a.valid)[g] = valid_mask(r0, r1, r2, r3);
         a.id[g] = (int32_t)(id_base + order);
@@ -443,12 +451,22 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
         a.invalid[g] = 0;
         if (a.merged) reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(0, 0, 0, 0);
         if (a.reset_indices) a.reset_indices[order] = g;
-        if (a.onehot) write_onehot_single_dyn(a.onehot_dtype, bd, a.onehot, g);
         order += 1;
+        }
+        if (a.onehot) {
+            uint32_t ballot = __ballot_sync(0xffffffffu, has);
+            while (ballot) {
+                const int src = __ffs((int)ballot) - 1;
+                ballot &= ballot - 1u;
+                const uint4 b = make_uint4(__shfl_sync(0xffffffffu, bd.x, src), __shfl_sync(0xffffffffu, bd.y, src),
+                                           __shfl_sync(0xffffffffu, bd.z, src), __shfl_sync(0xffffffffu, bd.w, src));
+                const long long gg = __shfl_sync(0xffffffffu, g, src);
+                write_onehot_warp_dyn(a.onehot_dtype, b, a.onehot, gg, lane);
+            }
+        }
     }
     // every flag this thread saw is now cleared (entry.fill(0), game_numba.py:638-639)
-    clear16 = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4 *>(a.terminated)[i] = clear16;
+    if (had_any) reinterpret_cast<uint4 *>(a.terminated)[i] = make_uint4(0, 0, 0, 0);
 }
 
 // ---- small stand-alone ops ------------------------------------------------------------------
