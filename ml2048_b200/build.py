@@ -31,9 +31,10 @@ def up_to_date() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+    if not force and up_to_date() and not os.environ.get("ML2048_NVCC_EXTRA"):
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, SRC]
+    extra = os.environ.get("ML2048_NVCC_EXTRA", "").split()  # experiment switches, e.g. -DML2048_STORE_DEFAULT
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
