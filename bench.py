@@ -51,6 +51,7 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--cpu-games", type=int, default=1 << 22, help="games per CPU step (bounded sample)")
     p.add_argument("--burn-in", type=int, default=BURN_IN, help="untimed steps from reset() to steady state")
+    p.add_argument("--clock-interval-ms", type=float, default=50.0, help="NVML sampling period during the timed region")
     return p.parse_args()
 
 
@@ -148,7 +149,7 @@ def run_reference_arm(args: argparse.Namespace) -> None:
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU every 10 ms through NVML while running."""
+    """Samples SM clock and throttle reasons of one GPU periodically through NVML while running."""
 
     REASONS = {
         0x8: "hw_slowdown",
@@ -158,9 +159,10 @@ class ClockSampler(threading.Thread):
         0x80: "hw_power_brake_slowdown",
     }
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, interval_s: float = 0.05):
         super().__init__(daemon=True)
         self.index = index
+        self.interval_s = interval_s
         self.samples: list[int] = []
         self.reasons: set[str] = set()
         self.max_mhz = None
@@ -198,7 +200,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.01)
+            self._halt.wait(self.interval_s)
 
     def stop(self) -> dict:
         self._halt.set()
@@ -300,9 +302,15 @@ def run_b200_arm(args: argparse.Namespace) -> None:
                                     dist.all_reduce(mx, op=dist.ReduceOp.MAX, async_op=True), sums, mx))
 
     run_steps(env, warm)
+    # first use of a torch op / an NCCL communicator loads kernels and connects ranks (tens to hundreds of ms):
+    # do both once before the timed region, which repeats them every STATS_EVERY steps
+    warm_stats = env.episode_stats_tensor()
+    if world > 1:
+        dist.all_reduce(warm_stats[:23].clone(), op=dist.ReduceOp.SUM)
+        dist.all_reduce(warm_stats[23:].clone(), op=dist.ReduceOp.MAX)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k_steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_interval_ms * 1e-3)
     barrier()
     sampler.start()
     start.record()
@@ -314,6 +322,11 @@ def run_b200_arm(args: argparse.Namespace) -> None:
     value = world * m * k_steps / (elapsed_ms * 1e-3)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / k_steps
     kernel_ms = max_over_ranks(kernel_ms)
+    gaps = sorted(kev[i][1].elapsed_time(kev[i + 1][0]) for i in range(k_steps - 1)) or [0.0]
+    prepare_ms = sum(gaps) / len(gaps)
+    if os.environ.get("ML2048_BENCH_DEBUG"):
+        print(f"[debug] prepare gaps ms: min {gaps[0]:.3f} p50 {gaps[len(gaps)//2]:.3f} p90 {gaps[int(len(gaps)*0.9)]:.3f} max {gaps[-1]:.3f}",
+              file=sys.stderr)
 
     peak, peak_src = load_peaks()
     bytes_per_launch = (BYTES_CORE + BYTES_ONEHOT_F32) * m
@@ -330,6 +343,7 @@ def run_b200_arm(args: argparse.Namespace) -> None:
         "bytes_per_env_step": BYTES_CORE + BYTES_ONEHOT_F32,
         "kernel_ms": kernel_ms,
         "kernel_share_of_step": kernel_ms / (elapsed_ms / k_steps),
+        "prepare_ms": prepare_ms,
     }
 
     for w0, w1, _, _ in pending:
