@@ -610,16 +610,24 @@ inline int launch_status()
 template <int kRng, bool kLog, bool kFull>
 int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
 {
+    // large batches: 768-thread blocks (one contiguous 768 KiB fp32 tile each); small batches need the parallelism
+    // of many 256-thread blocks (M = 2048 is 8 blocks instead of 3)
     constexpr int T = kOneHotStepThreads;
+    const bool big = a.num_games >= (1 << 19);
     const unsigned grid = (unsigned)((a.num_games + kStepThreads - 1) / kStepThreads);
-    const unsigned grid_oh = (unsigned)((a.num_games + T - 1) / T);
-    switch (a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE) {
+    const unsigned grid_big = (unsigned)((a.num_games + T - 1) / T);
+    const int onehot = a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE;
+    if (onehot < ML2048_ONEHOT_NONE || onehot > ML2048_ONEHOT_U8) return ML2048_E_ENUM;
+#define ML2048_LAUNCH(OH)                                                                              \
+    if (big) step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, 0, s>>>(a);                           \
+    else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
+    switch (onehot) {
     case ML2048_ONEHOT_NONE: step_kernel<kRng, kLog, ML2048_ONEHOT_NONE, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a); break;
-    case ML2048_ONEHOT_F32: step_kernel<kRng, kLog, ML2048_ONEHOT_F32, kFull, T><<<grid_oh, T, 0, s>>>(a); break;
-    case ML2048_ONEHOT_BF16: step_kernel<kRng, kLog, ML2048_ONEHOT_BF16, kFull, T><<<grid_oh, T, 0, s>>>(a); break;
-    case ML2048_ONEHOT_U8: step_kernel<kRng, kLog, ML2048_ONEHOT_U8, kFull, T><<<grid_oh, T, 0, s>>>(a); break;
-    default: return ML2048_E_ENUM;
+    case ML2048_ONEHOT_F32: ML2048_LAUNCH(ML2048_ONEHOT_F32); break;
+    case ML2048_ONEHOT_BF16: ML2048_LAUNCH(ML2048_ONEHOT_BF16); break;
+    default: ML2048_LAUNCH(ML2048_ONEHOT_U8); break;
     }
+#undef ML2048_LAUNCH
     return launch_status();
 }
 
