@@ -247,6 +247,7 @@ def run_b200_arm(args: argparse.Namespace) -> None:
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in ml2048_b200)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process: not bound"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -434,6 +435,7 @@ def run_b200_arm(args: argparse.Namespace) -> None:
                             f"all-reduced asynchronously every {STATS_EVERY} steps",
                 "l2": "inputs larger than L2 (boards 268 MB, one-hot 17 GB per GPU)",
                 "rng": "replay tables (bit-exact mode); actions: uniform over valid, Philox, in-kernel",
+                "host_affinity": numa,
             },
             "clocks": clocks,
             "e2e": e2e,
@@ -498,8 +500,37 @@ def measure_extras(ml2048_b200, torch, dev, seed: int) -> dict:
     return out
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the e2e arm are
+    allocated (first touch) on the NUMA node the GPU's PCIe root hangs off.  Harmless when it cannot be done."""
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to GPU {local_rank}"
+    except Exception as exc:  # noqa: BLE001
+        return f"not bound ({type(exc).__name__})"
+    return "not bound"
+
+
 def main() -> None:
     args = parse_args()
+    # exactly ONE line may reach stdout (the driver parses it): everything libraries print to fd 1 (NCCL's version
+    # banner, for one) is sent to stderr, and the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
