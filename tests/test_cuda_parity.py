@@ -560,3 +560,17 @@ def test_pipelined_host_step_matches_plain_step(ml, oracle):
             np.testing.assert_array_equal(r1[k], r0[k], err_msg=f"{k} step {t}")
     oh = env.observations_onehot().cpu().numpy()
     np.testing.assert_array_equal(oh, oracle.onehot(ref.observations()[0]).astype(np.uint8))
+
+
+def test_reset_midway_and_game_count_survives_reset(ml, oracle):
+    """reset(seed) rewinds tables and boards but `_game_count` keeps counting (game_numba.py:582 vs :606-617)."""
+    m = 300
+    ref = oracle.OracleVecGame(m, "rank", two_prob=0.25)
+    env = _make(ml, m, "rank", two_prob=0.25)
+    for seed, n in ((5, 90), (6, 150), (5, 40)):
+        ref.reset(seed)
+        env.reset(seed)
+        want = record_rollout(ref, n, action_seed=seed, wild=0.03, full=True)
+        got = record_rollout(env, n, actions=want["actions"], full=True)
+        compare_rollouts(got, want)
+    assert env._game_count == ref._game_count > 3 * m
