@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ML2048_ABI_VERSION 5
+#define ML2048_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define ML2048_API __attribute__((visibility("default")))
@@ -268,6 +268,22 @@ ML2048_API uint32_t ml2048_two_threshold(double two_prob);
 /* randperm (u8 [rows][16], each row a permutation of 0..15, game_numba.py:578,610) -> inverse-form keys used by
  * ml2048_step: the kernel picks the empty cell of smallest rank = the first empty cell of the table walk (:198-204) */
 ML2048_API int ml2048_pack_randperm_keys(const uint8_t *host_randperm, uint8_t *host_keys, int64_t rows);
+
+/* ---- host random schedule (no GPU work) -------------------------------------------------------------------------
+ * State of numpy's PCG64 bit generator (`Generator.bit_generator.state`), and the four draws the reference makes from
+ * it per prepare()/step(): random() (game_numba.py:622), integers(0, 1024) (:626, :670), permuted(axis=1) and
+ * random(float32) (:590-591).  Same bit stream as numpy; verified against the installed numpy at start-up. */
+typedef struct {
+    uint64_t state_hi, state_lo; /* 128-bit LCG state */
+    uint64_t inc_hi, inc_lo;     /* 128-bit increment */
+    int32_t has_uint32;          /* a buffered 32-bit half is pending */
+    uint32_t uinteger;           /* the buffered half */
+} ml2048_pcg64;
+
+ML2048_API double ml2048_pcg64_random(ml2048_pcg64 *g);
+ML2048_API int64_t ml2048_pcg64_integers(ml2048_pcg64 *g, int64_t high);
+ML2048_API void ml2048_pcg64_random_f32(ml2048_pcg64 *g, float *out, int64_t n);
+ML2048_API void ml2048_pcg64_permuted_rows_u8(ml2048_pcg64 *g, uint8_t *x, int64_t rows, int64_t cols);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libml2048_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 STATS_REPLICAS = 64
 STATS_WORDS = 24  # 20 histogram bins + episodes, score_sum, step_sum, score_max (unsigned long long each)
 
@@ -117,6 +117,19 @@ class PrepareArgs(C.Structure):
     ]
 
 
+class Pcg64(C.Structure):
+    """ml2048_pcg64"""
+
+    _fields_ = [
+        ("state_hi", C.c_uint64),
+        ("state_lo", C.c_uint64),
+        ("inc_hi", C.c_uint64),
+        ("inc_lo", C.c_uint64),
+        ("has_uint32", C.c_int32),
+        ("uinteger", C.c_uint32),
+    ]
+
+
 # every symbol include/ml2048_b200.h declares: (name, restype, argtypes)
 _VP, _I64, _I32, _U64, _U32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32
 SYMBOLS = {
@@ -136,6 +149,10 @@ SYMBOLS = {
     "ml2048_two_mask": (_U32, [_VP, C.c_double]),
     "ml2048_two_threshold": (_U32, [C.c_double]),
     "ml2048_pack_randperm_keys": (C.c_int, [_VP, _VP, _I64]),
+    "ml2048_pcg64_random": (C.c_double, [C.POINTER(Pcg64)]),
+    "ml2048_pcg64_integers": (_I64, [C.POINTER(Pcg64), _I64]),
+    "ml2048_pcg64_random_f32": (None, [C.POINTER(Pcg64), _VP, _I64]),
+    "ml2048_pcg64_permuted_rows_u8": (None, [C.POINTER(Pcg64), _VP, _I64, _I64]),
 }
 
 _lib = None

@@ -34,7 +34,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .host_rng import RAND_ROWS, NumpySchedule
+from .host_rng import RAND_ROWS, make_schedule
 from .rewards import reward_kind
 
 _ONEHOT = {
@@ -453,7 +453,7 @@ class VecGame:
 
     def reset(self, seed: Optional[int] = None, *, schedule: Any = None) -> None:
         """game_numba.py:606-617.  ``schedule`` (optional) replaces the numpy generator by recorded draws."""
-        self._schedule = schedule if schedule is not None else NumpySchedule(seed)
+        self._schedule = schedule if schedule is not None else make_schedule(seed)
         self._sched_len = self._sched_pos = 0
         self._pending_coin = None
         self._rand_step = 0
