@@ -283,6 +283,19 @@ ML2048_FN uint32_t kth_set_bit16(uint32_t mask, uint32_t k)
     return pos;
 }
 
+// The four 0/1 bytes of a valid-action word (left,right,up,down) as a 4-bit mask (multiply gathers bits 0,8,16,24)
+ML2048_FN uint32_t mask_bits4(uint32_t valid_word) { return (valid_word * 0x10204080u) >> 28; }
+
+// k-th (0-based) valid direction of a 4-bit mask, k < popc(bits): strip the k lowest set bits, take the next one
+ML2048_FN uint32_t kth_valid_action(uint32_t bits, uint32_t k)
+{
+    uint32_t t = bits;
+    t = (k > 0u) ? (t & (t - 1u)) : t;
+    t = (k > 1u) ? (t & (t - 1u)) : t;
+    t = (k > 2u) ? (t & (t - 1u)) : t;
+    return ffs32(t) - 1u;
+}
+
 // max tile exponent of a board (byte-wise max by compare-and-select; cells <= 0x7f)
 ML2048_FN uint32_t max_bytes(uint32_t a, uint32_t b)
 {

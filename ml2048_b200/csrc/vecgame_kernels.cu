@@ -182,14 +182,12 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
         uint32_t action;
         if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
             // uniform over the valid directions (policy/random.py:17-27); 0 when the game is over
-            const uint32_t vm = reinterpret_cast<const uint32_t *>(a.valid_in)[g];
-            const uint32_t bits = (vm & 1u) | ((vm >> 7) & 2u) | ((vm >> 14) & 4u) | ((vm >> 21) & 8u);
+            const uint32_t bits = mask_bits4(reinterpret_cast<const uint32_t *>(a.valid_in)[g]);
             const uint32_t nv = popc32(bits);
-            action = nv ? kth_set_bit16(bits, umulhi32(rnd.z, nv)) : 0u;
+            action = nv ? kth_valid_action(bits, umulhi32(rnd.z, nv)) : 0u;
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
         } else if (kFull && a.action_mode == ML2048_ACTIONS_FROM_LOGITS) {
-            const uint32_t vm = reinterpret_cast<const uint32_t *>(a.valid_in)[g];
-            const uint32_t bits = (vm & 1u) | ((vm >> 7) & 2u) | ((vm >> 14) & 4u) | ((vm >> 21) & 8u);
+            const uint32_t bits = mask_bits4(reinterpret_cast<const uint32_t *>(a.valid_in)[g]);
             const float4 lg = reinterpret_cast<const float4 *>(a.logits)[g];
             float lp;
             action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.z, lp);
@@ -213,7 +211,9 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
             // reward_fn (:728) and the score increment (:729-731)
             const uint32_t gain = fusion_gain(f);
             float reward;
-            if (a.reward_kind == ML2048_REWARD_IMPROVED) {
+            if (a.reward_kind == ML2048_REWARD_NORMAL) {
+                reward = (float)gain;
+            } else if (a.reward_kind == ML2048_REWARD_IMPROVED) {
                 // potential shaping on cell 0, game_numba.py:455-466 (all terms are exact integers in f32)
                 const uint32_t s0 = r0 & 0xffu, p0 = bd.x & 0xffu;
                 const int extra = (s0 ? (64 << s0) : 0) - (p0 ? (64 << p0) : 0);
@@ -527,10 +527,9 @@ __global__ void __launch_bounds__(kStepThreads) sample_random_valid_kernel(const
     const uint64_t slot = (uint64_t)(slot_base + g);
     const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)counter, (uint32_t)(counter >> 32),
                                     (uint32_t)seed, (uint32_t)(seed >> 32));
-    const uint32_t vm = valid[g];
-    const uint32_t bits = (vm & 1u) | ((vm >> 7) & 2u) | ((vm >> 14) & 4u) | ((vm >> 21) & 8u);
+    const uint32_t bits = mask_bits4(valid[g]);
     const uint32_t nv = popc32(bits);
-    actions[g] = (uint8_t)(nv ? kth_set_bit16(bits, umulhi32(rnd.z, nv)) : 0u);
+    actions[g] = (uint8_t)(nv ? kth_valid_action(bits, umulhi32(rnd.z, nv)) : 0u);
 }
 
 __global__ void __launch_bounds__(kStepThreads) sample_categorical_kernel(const float4 *logits, const uint32_t *valid, uint8_t *act8,

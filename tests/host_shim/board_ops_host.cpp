@@ -59,6 +59,10 @@ uint32_t hs_empties16(const uint8_t *board16)
 
 uint32_t hs_kth_set_bit16(uint32_t mask, uint32_t k) { return kth_set_bit16(mask, k); }
 
+uint32_t hs_mask_bits4(uint32_t valid_word) { return mask_bits4(valid_word); }
+
+uint32_t hs_kth_valid_action(uint32_t bits, uint32_t k) { return kth_valid_action(bits, k); }
+
 void hs_put_cell(uint8_t *board16, uint32_t cell, uint32_t value)
 {
     uint32_t r[4];

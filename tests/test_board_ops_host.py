@@ -154,6 +154,17 @@ def test_kth_set_bit(shim):
             assert shim.hs_kth_set_bit16(mask, k) == want
 
 
+def test_action_mask_helpers(shim):
+    shim.hs_mask_bits4.restype = ctypes.c_uint32
+    shim.hs_kth_valid_action.restype = ctypes.c_uint32
+    for bits in range(16):
+        word = sum(1 << (8 * i) for i in range(4) if bits >> i & 1)
+        assert shim.hs_mask_bits4(word) == bits
+        valid = [i for i in range(4) if bits >> i & 1]
+        for k, want in enumerate(valid):
+            assert shim.hs_kth_valid_action(bits, k) == want
+
+
 def test_philox_known_answers(shim):
     # Random123 kat_vectors: philox4x32-10
     cases = [
