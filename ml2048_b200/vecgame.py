@@ -933,11 +933,16 @@ class GraphedRollout:
     replay involves no host work besides the graph launch; the schedule window is refilled between replays when
     it runs low.  ``steps`` must be even (boards and masks are ping-pong buffers: an even number of steps ends in
     the buffers the graph started from).  Policy: uniform over valid actions, chosen in-kernel
-    (``actions=None``), or a caller-owned CUDA tensor of actions that the caller rewrites between replays of a
-    ONE-step-pair graph (``actions=tensor``, read by every captured step)."""
+    (``actions=None``), a caller-owned CUDA tensor of actions that the caller rewrites between replays
+    (``actions=tensor``, read by every captured step), or a torch policy INSIDE the graph: ``logits_fn(env)`` is
+    captured together with the environment kernels and must return the (M,4) float32 logits of the current
+    observations; the step kernel samples from them (``step_from_logits``).  With ``buffers`` (a
+    ``runner.RolloutBuffers``) step t of a replay writes its transition into row ``[use_index, t]`` and the sampled
+    action's log-probability into ``action_log_prob[use_index, t]`` -- the whole rollout of run_train3.py's epoch
+    (run_train3.py:175-183) becomes one graph launch."""
 
     def __init__(self, env: VecGame, steps: int, *, window: Optional[int] = None, actions: Optional[torch.Tensor] = None,
-                 return_actions: bool = False):
+                 return_actions: bool = False, logits_fn: Any = None, buffers: Any = None, use_index: int = 0):
         if steps <= 0 or steps % 2:
             raise ValueError(f"steps={steps}: must be a positive even number")
         self.env, self.steps = env, int(steps)
@@ -952,14 +957,28 @@ class GraphedRollout:
         side = torch.cuda.Stream(device=env.device)
         side.wait_stream(torch.cuda.current_stream(env.device))
         pos, cur = env._sched_pos, env._cur
+        if buffers is not None and buffers.shape[1] < self.steps:
+            raise ValueError("buffers hold fewer steps than one replay")
         with torch.cuda.stream(side):
+            if logits_fn is not None:
+                with torch.no_grad():
+                    for _ in range(3):  # warm the policy's kernels / workspaces outside the capture
+                        logits_fn(env)
+                side.synchronize()
             with torch.cuda.graph(self.graph, stream=side):
-                for _ in range(self.steps):
+                for t in range(self.steps):
                     env.prepare()
-                    if actions is None:
-                        env.step_random(return_actions=return_actions)
+                    record = buffers.row(use_index, t) if buffers is not None else None
+                    if logits_fn is not None:
+                        with torch.no_grad():
+                            logits = logits_fn(env).to(torch.float32).contiguous()
+                        lp = buffers["action_log_prob"][use_index, t] if buffers is not None else None
+                        env.step_from_logits(logits, log_prob_out=lp, record=record)
+                    elif actions is None:
+                        env.step_random(return_actions=return_actions or record is not None, record=record)
                     else:
-                        env.step(actions)
+                        env.step(actions, record=record)
+                env._set_record(None)
         torch.cuda.current_stream(env.device).wait_stream(side)
         # capturing executed nothing on the device: rewind the host mirrors
         env._sched_pos = pos

@@ -192,3 +192,40 @@ def test_device_runner_drives_a_reference_style_policy(ml, fused):
     assert torch.allclose(lp[nvalid > 0], -torch.log(nvalid.float())[nvalid > 0], atol=1e-6)
     stats = DeviceRunnerStats(env)
     assert stats.terminated_count > 0 and sum(c for _, c, _ in stats.summary()) == stats.terminated_count
+
+
+def test_whole_rollout_with_policy_as_one_cuda_graph(ml):
+    """env kernels + a torch policy + in-kernel sampling + transition recording captured as ONE graph:
+    replaying it equals the eager DeviceRunner rollout with the same policy and seeds."""
+    from ml2048_b200.ops import encode_onehot
+    from ml2048_b200.runner import DeviceRunner, RolloutBuffers
+
+    torch.manual_seed(0)
+    m, steps = 4096, 16
+    net = torch.nn.Sequential(torch.nn.Linear(256, 64), torch.nn.Tanh(), torch.nn.Linear(64, 4)).cuda()
+
+    def logits_fn(env):
+        return net(encode_onehot(env.observations()[0]).flatten(1))
+
+    class Policy:
+        def action_logits(self, state, valid):
+            return net(encode_onehot(state.to(torch.uint8)).flatten(1))
+
+    eager = ml.VecGame(m, ml.reward_fn_improved, output="torch", sync_free=True)
+    eager.reset(3)
+    buf_e = RolloutBuffers(1, steps, m, "cuda")
+    runner = DeviceRunner(eager, steps, buffers=buf_e, fused_sampler=True)
+    graphed = ml.VecGame(m, ml.reward_fn_improved, output="torch", sync_free=True)
+    graphed.reset(3)
+    buf_g = RolloutBuffers(1, steps, m, "cuda")
+    roll = ml.GraphedRollout(graphed, steps, window=steps * 4, logits_fn=logits_fn, buffers=buf_g)
+    for epoch in range(6):
+        runner.set_slot(0, 0)
+        runner.step_many(Policy(), steps)
+        roll.replay()
+        torch.cuda.synchronize()
+        for k in ("state", "action", "reward", "next_state", "terminated", "step", "valid_actions", "next_valid_actions"):
+            assert torch.equal(buf_g[k], buf_e[k]), (epoch, k)
+        assert torch.allclose(buf_g["action_log_prob"], buf_e["action_log_prob"], atol=1e-6)
+    assert torch.equal(graphed.observations()[0], eager.observations()[0])
+    assert graphed._game_count == eager._game_count
