@@ -72,6 +72,23 @@ def main():
           f"values+GAE: {t_gae/n*1e3:.2f} ms; finished episodes so far: {stats.terminated_count}")
     print("max-tile summary:", stats.summary()[:4])
 
+    # the same rollout (environment + policy + sampling + recording) captured once as a CUDA graph
+    env2 = ml2048_b200.VecGame(games, ml2048_b200.reward_fn_improved, output="torch", sync_free=True)
+    env2.reset(0)
+    buf2 = RolloutBuffers(1, steps, games, "cuda")
+
+    def logits_fn(e):
+        return policy.action_logits(e.observations()[0], None)
+
+    roll = ml2048_b200.GraphedRollout(env2, steps, window=steps * 16, logits_fn=logits_fn, buffers=buf2)
+    roll.replay(3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    roll.replay(a.epochs)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / a.epochs
+    print(f"rollout as ONE CUDA graph: {dt*1e3:.2f} ms per epoch = {dt/steps*1e6:.0f} us per runner step")
+
 
 if __name__ == "__main__":
     main()
