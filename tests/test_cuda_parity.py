@@ -574,3 +574,25 @@ def test_reset_midway_and_game_count_survives_reset(ml, oracle):
         got = record_rollout(env, n, actions=want["actions"], full=True)
         compare_rollouts(got, want)
     assert env._game_count == ref._game_count > 3 * m
+
+
+@pytest.mark.parametrize("scheduled", [False, True])
+def test_rand_step_wraps_at_table_size(ml, oracle, scheduled):
+    """`_rand_step >= 1024` forces a table refresh (game_numba.py:622-624).  It needs 1024 prepare() calls without a
+    refresh coin (probability 0.9^1024), so the counter is set by hand on both sides just below the limit."""
+    m, n = 777, 12
+    ref = oracle.OracleVecGame(m, "normal")
+    env = _make(ml, m, "normal")
+    ref.reset(21)
+    env.reset(21)
+    want0 = record_rollout(ref, 5, action_seed=1, wild=0.0, full=True)
+    got0 = record_rollout(env, 5, actions=want0["actions"], full=True)
+    compare_rollouts(got0, want0)
+    ref._rand_step = 1022
+    env._rand_step = 1022
+    if scheduled:
+        env.schedule_ahead(n)
+    want = record_rollout(ref, n, action_seed=2, wild=0.05, full=True)
+    got = record_rollout(env, n, actions=want["actions"], full=True)
+    compare_rollouts(got, want)
+    assert ref._rand_step < 20 and env._rand_step == ref._rand_step
