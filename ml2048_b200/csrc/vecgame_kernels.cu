@@ -383,13 +383,14 @@ __global__ void __launch_bounds__(1024) prepare_scan_kernel(int32_t *tile_counts
     }
 }
 
+// Reset pass over one tile of 4096 slots by one block.  `tile_offset` = finished games in earlier tiles, `id_base` = id of
+// the first game reset by this prepare().  Returns the number of games this tile reset (to every thread).
 template <int kRng>
-__global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml2048_prepare_args a, const int32_t *tile_offsets,
-                                                                     const int64_t *id_base_slot)
+__device__ __forceinline__ int apply_tile(const ml2048_prepare_args &a, int64_t tile, int64_t tile_offset, int64_t id_base,
+                                          int *warp_tot)
 {
-    __shared__ int warp_tot[kPrepThreads / 32];
     const int64_t n16 = (a.num_games + 15) / 16;
-    const int64_t i = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x;
+    const int64_t i = tile * kPrepThreads + threadIdx.x;
     uint32_t mask = 0u;
     if (i < n16) mask = flags16(reinterpret_cast<const uint4 *>(a.terminated)[i]);
     const int mine = __popc(mask);
@@ -418,8 +419,10 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
         philox_counter = e.philox_counter;
         perm_table += (int64_t)e.table * a.table_stride;
     }
-    int64_t order = (int64_t)tile_offsets[blockIdx.x] + wbase + inc - mine;  // rank among all reset slots
-    const int64_t id_base = *id_base_slot + (a.id_offset ? *a.id_offset : 0);
+    int tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPrepThreads / 32; ++w) tile_total += warp_tot[w];
+    int64_t order = tile_offset + wbase + inc - mine;  // rank among all reset slots
 
     // rounds: in each one every lane that still has a finished game resets one; the one-hot rows of the round
     // are then written by the whole warp, one game after the other
@@ -480,6 +483,37 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
     }
     // every flag this thread saw is now cleared (entry.fill(0), game_numba.py:638-639)
     if (had_any) reinterpret_cast<uint4 *>(a.terminated)[i] = make_uint4(0, 0, 0, 0);
+    return tile_total;
+}
+
+template <int kRng>
+__global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml2048_prepare_args a, const int32_t *tile_offsets,
+                                                                     const int64_t *id_base_slot)
+{
+    __shared__ int warp_tot[kPrepThreads / 32];
+    const int64_t id_base = *id_base_slot + (a.id_offset ? *a.id_offset : 0);
+    apply_tile<kRng>(a, blockIdx.x, tile_offsets[blockIdx.x], id_base, warp_tot);
+}
+
+// Small batches (a few tiles): count, scan and reset in ONE single-block launch -- the tiles are walked in order, so
+// the running total IS the exclusive scan.  Saves two launches per prepare(), which is what a 2048-game step costs.
+constexpr int kPrepSmallMaxGames = 8 * kPrepTile;
+
+template <int kRng>
+__global__ void __launch_bounds__(kPrepThreads) prepare_small_kernel(const ml2048_prepare_args a)
+{
+    __shared__ int warp_tot[kPrepThreads / 32];
+    const int tiles = (int)((a.num_games + kPrepTile - 1) / kPrepTile);
+    const int64_t id_base = *a.game_count;
+    int64_t running = 0;
+    for (int t = 0; t < tiles; ++t) {
+        running += apply_tile<kRng>(a, t, running, id_base, warp_tot);
+        __syncthreads();  // warp_tot is reused by the next tile
+    }
+    if (threadIdx.x == 0) {
+        *a.game_count = id_base + running;
+        *a.reset_count = running;
+    }
 }
 
 // ---- small stand-alone ops ------------------------------------------------------------------
@@ -759,7 +793,17 @@ int ml2048_prepare_apply(const ml2048_prepare_args *args, void *stream)
 
 int ml2048_prepare(const ml2048_prepare_args *args, void *stream)
 {
-    const int rc = ml2048_prepare_count(args, stream);
+    int rc = check_prepare_args(args);
+    if (rc) return rc;
+    if (args->num_games <= kPrepSmallMaxGames && !args->id_offset) {
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        if (args->rng_mode == ML2048_RNG_REPLAY)
+            prepare_small_kernel<ML2048_RNG_REPLAY><<<1, kPrepThreads, 0, s>>>(*args);
+        else
+            prepare_small_kernel<ML2048_RNG_PHILOX><<<1, kPrepThreads, 0, s>>>(*args);
+        return launch_status();
+    }
+    rc = ml2048_prepare_count(args, stream);
     if (rc) return rc;
     return ml2048_prepare_apply(args, stream);
 }
