@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_apply_kernel(const ml204
 
 // Small batches (a few tiles): count, scan and reset in ONE single-block launch -- the tiles are walked in order, so
 // the running total IS the exclusive scan.  Saves two launches per prepare(), which is what a 2048-game step costs.
-constexpr int kPrepSmallMaxGames = 8 * kPrepTile;
+constexpr int kPrepSmallMaxGames = 2 * kPrepTile;  // beyond two tiles the serial walk loses to the three-kernel path
 
 template <int kRng>
 __global__ void __launch_bounds__(kPrepThreads) prepare_small_kernel(const ml2048_prepare_args a)
