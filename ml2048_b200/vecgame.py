@@ -242,6 +242,7 @@ class VecGame:
         self._tables_host = np.zeros((2, RAND_ROWS, 16), dtype=np.uint8)  # staging: randperm + its inverse-form keys
         self._record_active = False
         self._keep_record = None
+        self._obs_cache = None
         self._sched_len = 0   # entries of the device-resident schedule (0 = eager mode: host draws per call)
         self._sched_pos = 0   # entries consumed so far (host mirror of the device cursor)
         self._rand_step = 0
@@ -328,16 +329,32 @@ class VecGame:
         p.reset_indices = self._p(self._reset_indices_dev)
         p.scratch = self._p(self._scratch)
 
-    def _to_host(self, t: torch.Tensor, key: Optional[str] = None) -> np.ndarray:
-        """D2H through a pinned staging buffer owned by this environment (reused per field)."""
-        name = key or f"_anon{t.data_ptr()}"
+    def _pinned(self, name: str, t: torch.Tensor) -> torch.Tensor:
         buf = self._host.get(name)
         if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
             buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             self._host[name] = buf
+        return buf
+
+    def _to_host(self, t: torch.Tensor, key: Optional[str] = None) -> np.ndarray:
+        """D2H through a pinned staging buffer owned by this environment (reused per field)."""
+        buf = self._pinned(key or f"_anon{t.data_ptr()}", t)
         buf.copy_(t, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return buf.numpy()
+
+    def _to_host_many(self, fields: dict[str, torch.Tensor]) -> dict[str, np.ndarray]:
+        """Several D2H copies behind ONE synchronisation (small batches are latency-, not bandwidth-bound)."""
+        bufs = {k: self._pinned(k, t) for k, t in fields.items()}
+        for k, t in fields.items():
+            bufs[k].copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: b.numpy() for k, b in bufs.items()}
+
+    # NumPy (drop-in) mode, small batches: a runner step is dominated by the ~12 us each host<->device round trip
+    # costs, so prepare() and step() fetch everything the reference's callers read in one go (one sync each)
+    # instead of one copy + sync per field.  Large batches stay lazy: there the copies are PCIe-bandwidth bound.
+    _EAGER_HOST_MAX_GAMES = 1 << 17
 
     def _device_field(self, key: str) -> torch.Tensor:
         cur = self._cur
@@ -473,9 +490,13 @@ class VecGame:
             self._onehot[:, 0, :] = 1  # an all-empty board encodes as class 0 everywhere
         self._stats_dev.zero_()
         self._cur = 0
+        self._obs_cache = None
 
     def observations(self):
         """game_numba.py:586-587: (board (M,16) u8, valid_actions (M,4) u8)."""
+        cached = self._obs_cache
+        if cached is not None:
+            return cached
         return self._fetch("state"), self._fetch("valid_actions")
 
     def observations_onehot(self) -> torch.Tensor:
@@ -518,8 +539,15 @@ class VecGame:
                 _lib.check(self._lib.ml2048_prepare(C.byref(p), stream), "ml2048_prepare")
             else:
                 self._prepare_sharded(p, stream)
+        self._obs_cache = None
         if self._sync_free:
             return (None,)
+        if self._output == "numpy" and self._size <= self._EAGER_HOST_MAX_GAMES:
+            # count, index list and the post-reset observations behind one synchronisation
+            got = self._to_host_many({"_reset_count": self._reset_count_dev, "_reset_indices": self._reset_indices_dev,
+                                      "state": self._board[cur], "valid_actions": self._valid[cur]})
+            self._obs_cache = (got["state"], got["valid_actions"])
+            return (got["_reset_indices"][: int(got["_reset_count"][0])].copy(),)
         n = int(self._reset_count_dev.item())
         idx = self._reset_indices_dev[:n]
         if self._output == "torch":
@@ -549,14 +577,42 @@ class VecGame:
         if fetch and not record and self._can_pipeline(actions):
             return self._step_pipelined(actions, tuple(fetch))
         a = self._step_args
-        dev_actions, a.action_dtype = self._stage_actions(actions)
+        eager_host = (self._output == "numpy" and self._size <= self._EAGER_HOST_MAX_GAMES and not self._sync_free
+                      and isinstance(actions, np.ndarray))
+        if eager_host:
+            dev_actions, a.action_dtype = self._stage_actions_pinned(actions)
+        else:
+            dev_actions, a.action_dtype = self._stage_actions(actions)
         a.action_mode = _lib.ACTIONS_GIVEN
         a.actions = dev_actions.data_ptr()
         a.actions_out = None
         self._set_record(record)
         self._launch_step()
         self._keepalive = dev_actions
-        return VecStepResult(self)
+        res = VecStepResult(self)
+        if eager_host:
+            # every field the reference's callers read (runner.py:165, replay.py:170-173, run_train3.py:138-149): one sync
+            keys = [k for k in VecStepResult.KEYS if k != "merged" or self._merged is not None]
+            for k, v in self._to_host_many({k: self._device_field(k) for k in keys}).items():
+                dict.__setitem__(res, k, v)
+        return res
+
+    def _stage_actions_pinned(self, actions: np.ndarray) -> tuple[torch.Tensor, int]:
+        """Host actions -> pinned staging -> asynchronous H2D (no pageable-copy synchronisation)."""
+        if actions.dtype not in (np.int64, np.int32, np.uint8, np.int8):
+            actions = actions.astype(np.int64)
+        if actions.dtype == np.int8:
+            actions = actions.view(np.uint8)
+        tdtype = {np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8}[actions.dtype]
+        stage = self._host.get("_actions_stage")
+        if stage is None or stage.dtype != tdtype:
+            stage = torch.empty((self._size,), dtype=tdtype, pin_memory=True)
+            self._host["_actions_stage"] = stage
+            self._actions_stage_dev = torch.empty((self._size,), dtype=tdtype, device=self.device)
+        stage.numpy()[...] = actions
+        self._actions_stage_dev.copy_(stage, non_blocking=True)
+        code = {torch.int64: _lib.ACT_I64, torch.int32: _lib.ACT_I32, torch.uint8: _lib.ACT_U8}[tdtype]
+        return self._actions_stage_dev, code
 
     def step_from_logits(self, logits: torch.Tensor, *, log_prob_out: Optional[torch.Tensor] = None,
                          record: Optional[dict] = None) -> VecStepResult:
@@ -669,6 +725,7 @@ class VecGame:
     def _launch_step(self) -> None:
         a = self._step_args
         cur = self._cur
+        self._obs_cache = None
         if self._sched_len:
             if self._sched_pos >= self._sched_len:
                 raise RuntimeError("the device schedule is used up: call prepare() (or schedule_ahead) first")
@@ -866,6 +923,7 @@ class VecGame:
         self._table_slot = host.get("table_slot", 0)
         self._pending_coin = host.get("pending_coin")
         self._sched_len = self._sched_pos = 0
+        self._obs_cache = None
 
     def enable_episode_log(self, capacity: int, id_base: int = 0) -> None:
         """Record (steps, score, max tile) of every finished game whose id lies in [id_base, id_base+capacity),
