@@ -200,16 +200,28 @@ class VecGame:
         m, dev = self._size, self.device
         pad = (m + 15) // 16 * 16
         with torch.cuda.device(dev):
-            self._board = torch.zeros((2, m, 16), dtype=torch.uint8, device=dev)
-            self._valid = torch.zeros((2, m, 4), dtype=torch.uint8, device=dev)
-            self._id = torch.zeros((m,), dtype=torch.int32, device=dev)
-            self._step = torch.zeros((m,), dtype=torch.int32, device=dev)
-            self._score = torch.zeros((m,), dtype=torch.float32, device=dev)
-            self._reward = torch.zeros((m,), dtype=torch.float32, device=dev)
-            self._terminated_padded = torch.zeros((pad,), dtype=torch.uint8, device=dev)
+            # All per-game state the reference's callers can read lives in ONE arena (sub-buffers 256-byte aligned), so
+            # that the NumPy drop-in mode can mirror it to the host with a single copy (see _mirror_to_host).
+            layout = [("_reset_count_dev", torch.int64, (1,)), ("_game_count_dev", torch.int64, (1,)),  # count survives reset(), :582
+                      ("_reset_indices_dev", torch.int64, (m,)), ("_board", torch.uint8, (2, m, 16)),
+                      ("_valid", torch.uint8, (2, m, 4)), ("_id", torch.int32, (m,)), ("_step", torch.int32, (m,)),
+                      ("_score", torch.float32, (m,)), ("_reward", torch.float32, (m,)),
+                      ("_terminated_padded", torch.uint8, (pad,)), ("_invalid", torch.uint8, (m,))]
+            if track_merged:
+                layout.append(("_merged", torch.uint8, (m, 16)))
+            offsets, total = {}, 0
+            for name, dtype, shape in layout:
+                nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+                offsets[name] = (total, nbytes, dtype, shape)
+                total += (nbytes + 255) // 256 * 256
+            self._arena = torch.zeros((total,), dtype=torch.uint8, device=dev)
+            self._arena_layout = offsets
+            self._arena_host = None  # pinned mirror, allocated on first use
+            for name, (off, nbytes, dtype, shape) in offsets.items():
+                setattr(self, name, self._arena[off:off + nbytes].view(dtype).view(shape))
             self._terminated = self._terminated_padded[:m]
-            self._invalid = torch.zeros((m,), dtype=torch.uint8, device=dev)
-            self._merged = torch.zeros((m, 16), dtype=torch.uint8, device=dev) if track_merged else None
+            if not track_merged:
+                self._merged = None
             self._onehot = torch.zeros((m, 16, 16), dtype=onehot_dtype, device=dev) if onehot_dtype is not None else None
             self._actions_dev = torch.zeros((m,), dtype=torch.int64, device=dev)  # staging for host actions
             self._actions_out = torch.zeros((m,), dtype=torch.uint8, device=dev)
@@ -220,9 +232,6 @@ class VecGame:
             self._table_slot = 0
             self._sched_dev = None                       # int64 (L, 4): ml2048_sched_entry[L]
             self._sched_cursor_dev = torch.zeros((2,), dtype=torch.int64, device=dev)  # ping-pong like the boards
-            self._game_count_dev = torch.zeros((1,), dtype=torch.int64, device=dev)  # survives reset(), :582
-            self._reset_count_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
-            self._reset_indices_dev = torch.zeros((m,), dtype=torch.int64, device=dev)
             self._id_offset_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
             n_scratch = int(self._lib.ml2048_prepare_scratch_ints(m))
             self._scratch = torch.zeros((n_scratch,), dtype=torch.int32, device=dev)
@@ -352,9 +361,37 @@ class VecGame:
         return {k: b.numpy() for k, b in bufs.items()}
 
     # NumPy (drop-in) mode, small batches: a runner step is dominated by the ~12 us each host<->device round trip
-    # costs, so prepare() and step() fetch everything the reference's callers read in one go (one sync each)
-    # instead of one copy + sync per field.  Large batches stay lazy: there the copies are PCIe-bandwidth bound.
+    # costs, so prepare() and step() mirror the WHOLE state arena to the host with one copy and one sync instead
+    # of one copy + sync per field.  Large batches stay lazy: there the copies are PCIe-bandwidth bound.
     _EAGER_HOST_MAX_GAMES = 1 << 17
+
+    def _mirror_to_host(self) -> dict[str, np.ndarray]:
+        """One D2H copy of the state arena into its pinned host mirror; returns NumPy views of the mirror by name."""
+        if self._arena_host is None:
+            self._arena_host = torch.empty(self._arena.shape, dtype=torch.uint8, pin_memory=True)
+            flat = self._arena_host.numpy()
+            views = {}
+            for name, (off, nbytes, dtype, shape) in self._arena_layout.items():
+                npdt = {torch.int64: np.int64, torch.int32: np.int32, torch.float32: np.float32, torch.uint8: np.uint8}[dtype]
+                views[name] = flat[off:off + nbytes].view(npdt).reshape(shape)
+            self._mirror = views
+        self._arena_host.copy_(self._arena, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._mirror
+
+    def _mirror_field(self, views: dict[str, np.ndarray], key: str) -> np.ndarray:
+        cur = self._cur
+        if key == "state":
+            return views["_board"][cur]
+        if key == "valid_actions":
+            return views["_valid"][cur]
+        if key == "prev_state":
+            return views["_board"][1 - cur]
+        if key == "prev_valid_actions":
+            return views["_valid"][1 - cur]
+        if key == "terminated":
+            return views["_terminated_padded"][: self._size]
+        return views["_" + key]
 
     def _device_field(self, key: str) -> torch.Tensor:
         cur = self._cur
@@ -544,10 +581,9 @@ class VecGame:
             return (None,)
         if self._output == "numpy" and self._size <= self._EAGER_HOST_MAX_GAMES:
             # count, index list and the post-reset observations behind one synchronisation
-            got = self._to_host_many({"_reset_count": self._reset_count_dev, "_reset_indices": self._reset_indices_dev,
-                                      "state": self._board[cur], "valid_actions": self._valid[cur]})
-            self._obs_cache = (got["state"], got["valid_actions"])
-            return (got["_reset_indices"][: int(got["_reset_count"][0])].copy(),)
+            views = self._mirror_to_host()
+            self._obs_cache = (views["_board"][cur], views["_valid"][cur])
+            return (views["_reset_indices_dev"][: int(views["_reset_count_dev"][0])].copy(),)
         n = int(self._reset_count_dev.item())
         idx = self._reset_indices_dev[:n]
         if self._output == "torch":
@@ -592,9 +628,10 @@ class VecGame:
         res = VecStepResult(self)
         if eager_host:
             # every field the reference's callers read (runner.py:165, replay.py:170-173, run_train3.py:138-149): one sync
-            keys = [k for k in VecStepResult.KEYS if k != "merged" or self._merged is not None]
-            for k, v in self._to_host_many({k: self._device_field(k) for k in keys}).items():
-                dict.__setitem__(res, k, v)
+            views = self._mirror_to_host()
+            for k in VecStepResult.KEYS:
+                if k != "merged" or self._merged is not None:
+                    dict.__setitem__(res, k, self._mirror_field(views, k))
         return res
 
     def _stage_actions_pinned(self, actions: np.ndarray) -> tuple[torch.Tensor, int]:
