@@ -363,7 +363,7 @@ class VecGame:
     # NumPy (drop-in) mode, small batches: a runner step is dominated by the ~12 us each host<->device round trip
     # costs, so prepare() and step() mirror the WHOLE state arena to the host with one copy and one sync instead
     # of one copy + sync per field.  Large batches stay lazy: there the copies are PCIe-bandwidth bound.
-    _EAGER_HOST_MAX_GAMES = 1 << 17
+    _EAGER_HOST_MAX_GAMES = 1 << 15
 
     def _mirror_to_host(self) -> dict[str, np.ndarray]:
         """One D2H copy of the state arena into its pinned host mirror; returns NumPy views of the mirror by name."""
