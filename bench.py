@@ -398,12 +398,15 @@ def run_b200_arm(args: argparse.Namespace) -> None:
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms))
+        # the replayed host actions were recorded from this very trajectory, so every one of them must be a valid move
+        invalid_last = int(env._invalid.sum().item())
         e2e = {
             "value": world * m * k_steps / (e2e_ms * 1e-3),
             "unit": UNIT,
             "h2d_bytes_per_step": int(m * world),
             "d2h_bytes_per_step": int(d2h / k_steps * world),
             "ms_per_step": e2e_ms / k_steps,
+            "invalid_moves_in_last_step": invalid_last,
             "api": "VecGame.prepare() -> (indices,); VecGame.step(uint8 actions in pinned host memory) -> "
                    "state, valid_actions, reward, terminated as host arrays",
         }
