@@ -400,6 +400,14 @@ def run_b200_arm(args: argparse.Namespace) -> None:
         e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms))
         # the replayed host actions were recorded from this very trajectory, so every one of them must be a valid move
         invalid_last = int(env._invalid.sum().item())
+        # second regime: the policy lives on the GPU, the host only reads reward + terminated (5 B per game)
+        light_steps = min(k_steps, 20)
+        t0 = time.perf_counter()
+        for t in range(warm, warm + light_steps):
+            env.prepare()
+            res = env.step(host_actions[t], fetch=("reward", "terminated"))
+        torch.cuda.synchronize()
+        light_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / light_steps
         e2e = {
             "value": world * m * k_steps / (e2e_ms * 1e-3),
             "unit": UNIT,
@@ -407,6 +415,8 @@ def run_b200_arm(args: argparse.Namespace) -> None:
             "d2h_bytes_per_step": int(d2h / k_steps * world),
             "ms_per_step": e2e_ms / k_steps,
             "invalid_moves_in_last_step": invalid_last,
+            "light": {"value": world * m / (light_ms * 1e-3), "ms_per_step": light_ms,
+                      "d2h": "reward + terminated only (5 B per game); observations stay on the device"},
             "api": "VecGame.prepare() -> (indices,); VecGame.step(uint8 actions in pinned host memory) -> "
                    "state, valid_actions, reward, terminated as host arrays",
         }
