@@ -372,7 +372,6 @@ def run_b200_arm(args: argparse.Namespace) -> None:
             host_actions[t].copy_(env._actions_out, non_blocking=True)
         torch.cuda.synchronize()
         env.load_state_dict(snapshot)
-        del snapshot
         env.configure(output="numpy", sync_free=False)
         consumed = 0
 
@@ -401,13 +400,20 @@ def run_b200_arm(args: argparse.Namespace) -> None:
         # the replayed host actions were recorded from this very trajectory, so every one of them must be a valid move
         invalid_last = int(env._invalid.sum().item())
         # second regime: the policy lives on the GPU, the host only reads reward + terminated (5 B per game)
-        light_steps = min(k_steps, 20)
+        env.load_state_dict(snapshot)  # rewind again: the recorded actions belong to this trajectory
+        del snapshot
+        light_steps = min(total - 3, 20)
+        for t in range(3):
+            env.prepare()
+            env.step(host_actions[t], fetch=("reward", "terminated"))
+        barrier()
         t0 = time.perf_counter()
-        for t in range(warm, warm + light_steps):
+        for t in range(3, 3 + light_steps):
             env.prepare()
             res = env.step(host_actions[t], fetch=("reward", "terminated"))
         torch.cuda.synchronize()
         light_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / light_steps
+        invalid_last = max(invalid_last, int(env._invalid.sum().item()))
         e2e = {
             "value": world * m * k_steps / (e2e_ms * 1e-3),
             "unit": UNIT,
