@@ -116,6 +116,47 @@ __device__ __forceinline__ void write_onehot_tile(const uint4 *sboards, int game
         store_streaming(out + (int64_t)g * kPer + piece, P::make(sboards, g, piece));
 }
 
+// The same tile written through the TMA bulk-copy engine (experiment switch -DML2048_ONEHOT_TMA, 768-thread variant only):
+// the block assembles 48 games (48 KiB in fp32) at a time in shared memory and one elected thread hands the chunk to
+// `cp.async.bulk.global.shared::cta`, double-buffered, so the SM issues shared-memory stores instead of global ones and the
+// copy engine streams the tile to L2/HBM.
+#if defined(ML2048_ONEHOT_TMA)
+constexpr int kTmaChunkGames = 48;
+
+template <int kDtype, int kThreads>
+__device__ __forceinline__ void write_onehot_tile_tma(const uint4 *sboards, int games, void *out_base, int64_t first_game,
+                                                      uint4 *stage /* [2][kTmaChunkGames * kPer] */)
+{
+    using P = OneHotPiece<kDtype>;
+    constexpr int kPer = P::kPiecesPerGame;
+    char *out = reinterpret_cast<char *>(out_base) + first_game * kPer * 16;
+    int buf = 0;
+    for (int g0 = 0; g0 < games; g0 += kTmaChunkGames, buf ^= 1) {
+        const int n = min(kTmaChunkGames, games - g0);
+        uint4 *dst = stage + buf * (kTmaChunkGames * kPer);
+        // the bulk copy that last read this buffer (two chunks ago) must have finished reading it
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        for (int q = threadIdx.x; q < n * kPer; q += kThreads) {
+            const typename P::vec v = P::make(sboards, g0 + q / kPer, q % kPer);
+            dst[q] = *reinterpret_cast<const uint4 *>(&v);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(dst);
+            const uint32_t bytes = (uint32_t)(n * kPer * 16);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (int64_t)g0 * kPer * 16), "r"(src),
+                         "r"(bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
+    __syncthreads();
+}
+#endif
+
 // One game's one-hot row written by a whole warp (reset path): lane l stores pieces l, l+32, ... so that one warp
 // instruction covers up to 512 contiguous bytes.
 template <int kDtype>
@@ -152,6 +193,9 @@ template <int kRng, bool kLog, int kOneHot, bool kFull, int kThreads>
 __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a)
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kThreads : 1];
+#if defined(ML2048_ONEHOT_TMA)
+    extern __shared__ __align__(128) uint4 tma_stage[];  // [2][48 games x pieces] when launched with dynamic shared memory
+#endif
     const int64_t block_first = (int64_t)blockIdx.x * kThreads;
     const int64_t g = block_first + threadIdx.x;
     const bool live = g < a.num_games;
@@ -310,8 +354,13 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
         __syncthreads();
         const int64_t remaining = a.num_games - block_first;
         const int games = remaining < kThreads ? (int)remaining : kThreads;
-        write_onehot_tile<kOneHot == ML2048_ONEHOT_NONE ? ML2048_ONEHOT_F32 : kOneHot, kThreads>(sboards, games, a.onehot_out,
-                                                                                                  block_first);
+        constexpr int kOH = kOneHot == ML2048_ONEHOT_NONE ? ML2048_ONEHOT_F32 : kOneHot;
+#if defined(ML2048_ONEHOT_TMA)
+        if (kThreads == kOneHotStepThreads)
+            write_onehot_tile_tma<kOH, kThreads>(sboards, games, a.onehot_out, block_first, tma_stage);
+        else
+#endif
+            write_onehot_tile<kOH, kThreads>(sboards, games, a.onehot_out, block_first);
     }
 }
 
@@ -651,9 +700,18 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
     const unsigned grid_big = (unsigned)((a.num_games + T - 1) / T);
     const int onehot = a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE;
     if (onehot < ML2048_ONEHOT_NONE || onehot > ML2048_ONEHOT_U8) return ML2048_E_ENUM;
+#if defined(ML2048_ONEHOT_TMA)
+#define ML2048_LAUNCH(OH)                                                                              \
+    if (big) {                                                                                         \
+        const int smem = 2 * kTmaChunkGames * OneHotPiece<OH>::kPiecesPerGame * 16;                    \
+        cudaFuncSetAttribute(step_kernel<kRng, kLog, OH, kFull, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, smem, s>>>(a);                             \
+    } else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
+#else
 #define ML2048_LAUNCH(OH)                                                                              \
     if (big) step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, 0, s>>>(a);                           \
     else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
+#endif
     switch (onehot) {
     case ML2048_ONEHOT_NONE: step_kernel<kRng, kLog, ML2048_ONEHOT_NONE, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a); break;
     case ML2048_ONEHOT_F32: ML2048_LAUNCH(ML2048_ONEHOT_F32); break;

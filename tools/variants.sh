@@ -1,10 +1,11 @@
+# Build-variant experiments (run on the GPU box): each variant is built, parity-checked on the one-hot tests, and timed.
 set -e
 cd $GRAFT_REPO_ROOT
-for v in "-DML2048_STORE_DEFAULT" "-DML2048_STORE_DEFAULT -DML2048_STEP_THREADS=512" "-DML2048_STORE_DEFAULT -DML2048_STEP_THREADS=1024" "-DML2048_STORE_DEFAULT -DML2048_STEP_THREADS=768"; do
-  ML2048_NVCC_EXTRA="$v" python -m ml2048_b200.build >/dev/null 2>&1
+for v in "-DML2048_ONEHOT_TMA" ""; do
+  ML2048_NVCC_EXTRA="$v" python -m ml2048_b200.build >/dev/null 2>&1 || python -c "from ml2048_b200 import build; build.build(force=True)"
   echo "variant [$v]"
-  for oh in f32 bf16 u8 none; do
-    if [ $oh = none ]; then python tools/profile_core.py --steps 20 | sed 's/.*prepare/prepare/' | cut -c1-90; else
-    python tools/profile_core.py --onehot $oh --steps 20 | sed 's/.*prepare/prepare/' | cut -c1-90; fi
+  timeout 600 python -m pytest tests/test_cuda_parity.py -q -x -k "onehot or properties or golden" 2>&1 | tail -2
+  for oh in f32 bf16 u8; do
+    python tools/profile_core.py --onehot $oh --steps 30 --burn-in 256 | sed 's/.*prepare/prepare/' | cut -c1-100
   done
 done
