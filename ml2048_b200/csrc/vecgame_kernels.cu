@@ -129,22 +129,26 @@ __device__ __forceinline__ void write_onehot_tile(const uint4 *sboards, int game
 #ifndef ML2048_TMA_CHUNK_BYTES
 #define ML2048_TMA_CHUNK_BYTES 49152
 #endif
-constexpr int kTmaChunkBytes = ML2048_TMA_CHUNK_BYTES;  // per bulk copy; two of them are staged per block
+constexpr int kTmaChunkBytes = ML2048_TMA_CHUNK_BYTES;  // per bulk copy
+#ifndef ML2048_TMA_STAGES
+#define ML2048_TMA_STAGES 2
+#endif
+constexpr int kTmaStages = ML2048_TMA_STAGES;           // chunks staged per block
 
 template <int kDtype, int kThreads>
 __device__ __forceinline__ void write_onehot_tile_tma(const uint4 *sboards, int games, void *out_base, int64_t first_game,
-                                                      uint4 *stage /* [2][kTmaChunkBytes / 16] */)
+                                                      uint4 *stage /* [kTmaStages][kTmaChunkBytes / 16] */)
 {
     using P = OneHotPiece<kDtype>;
     constexpr int kPer = P::kPiecesPerGame;
     constexpr int kTmaChunkGames = kTmaChunkBytes / (kPer * 16);
     char *out = reinterpret_cast<char *>(out_base) + first_game * kPer * 16;
     int buf = 0;
-    for (int g0 = 0; g0 < games; g0 += kTmaChunkGames, buf ^= 1) {
+    for (int g0 = 0; g0 < games; g0 += kTmaChunkGames, buf = (buf + 1 == kTmaStages) ? 0 : buf + 1) {
         const int n = min(kTmaChunkGames, games - g0);
         uint4 *dst = stage + buf * (kTmaChunkGames * kPer);
         // the bulk copy that last read this buffer (two chunks ago) must have finished reading it
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kTmaStages - 1) : "memory");
         __syncthreads();
         for (int q = threadIdx.x; q < n * kPer; q += kThreads) {
             const typename P::vec v = P::make(sboards, g0 + q / kPer, q % kPer);
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kThreads : 1];
 #if defined(ML2048_ONEHOT_TMA)
-    extern __shared__ __align__(128) uint4 tma_stage[];  // [2][kTmaChunkBytes] when launched with dynamic shared memory
+    extern __shared__ __align__(128) uint4 tma_stage[];  // [kTmaStages][kTmaChunkBytes] when launched with dynamic shared memory
 #endif
     const int64_t block_first = (int64_t)blockIdx.x * kThreads;
     const int64_t g = block_first + threadIdx.x;
@@ -712,7 +716,7 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
 #if defined(ML2048_ONEHOT_TMA)
 #define ML2048_LAUNCH(OH)                                                                              \
     if (big) {                                                                                         \
-        const int smem = 2 * kTmaChunkBytes;                                                           \
+        const int smem = kTmaStages * kTmaChunkBytes;                                                  \
         cudaFuncSetAttribute(step_kernel<kRng, kLog, OH, kFull, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, smem, s>>>(a);                             \
     } else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
