@@ -5,7 +5,8 @@ Reference surface kept (reference: src/ml2048/game_numba.py): ``VecGame``, ``Vec
 """
 
 from .rewards import reward_fn_improved, reward_fn_maxcell, reward_fn_normal, reward_fn_rank
-from .vecgame import GraphedRollout, VecGame, VecStepResult
+from .graph import GraphedRollout
+from .vecgame import VecGame, VecStepResult
 
 STEP_LEFT, STEP_RIGHT, STEP_UP, STEP_DOWN = 0, 1, 2, 3  # src/ml2048/game.py:14-17
 
