@@ -247,7 +247,7 @@ class VecGame:
         # host copies of the random tables, as in the reference (game_numba.py:577-580)
         self._randperm = np.empty((RAND_ROWS, 16), dtype=np.uint8)
         self._randfloat = np.empty((RAND_ROWS,), dtype=np.float32)
-        self._tables_host = np.zeros((2, RAND_ROWS, 16), dtype=np.uint8)  # staging: randperm + its inverse-form keys
+        self._tables_pin = None  # pinned staging ring for table uploads, allocated on first use
         self._record_active = False
         self._keep_record = None
         self._obs_cache = None
@@ -410,13 +410,26 @@ class VecGame:
     def _upload_tables(self) -> None:
         """Tables changed on the host: ship the permutations (16 KiB) and fold the 2-vs-4 uniforms into
         a 16-bit mask (only randfloat[0:16] is ever read, indexed by CELL: game_numba.py:207)."""
-        _lib.check(self._lib.ml2048_pack_randperm_keys(self._randperm.ctypes.data, self._tables_host[1].ctypes.data, RAND_ROWS),
+        # Staged through a small ring of pinned buffers so that the upload (32 KiB, ~10 % of prepare() calls) is an
+        # asynchronous copy: a pageable copy would make the host wait for everything queued on the stream.
+        if self._tables_pin is None:
+            self._tables_pin = torch.empty((4, 2, RAND_ROWS, 16), dtype=torch.uint8, pin_memory=True)
+            self._tables_pin_np = self._tables_pin.numpy()
+            self._tables_pin_events = [None] * 4
+            self._tables_pin_next = 0
+        k = self._tables_pin_next
+        self._tables_pin_next = (k + 1) % 4
+        if self._tables_pin_events[k] is not None:
+            self._tables_pin_events[k].synchronize()  # the copy that last used this staging slot (4 refreshes ago)
+        stage = self._tables_pin_np[k]
+        stage[0] = self._randperm
+        _lib.check(self._lib.ml2048_pack_randperm_keys(self._randperm.ctypes.data, stage[1].ctypes.data, RAND_ROWS),
                    "ml2048_pack_randperm_keys")
-        self._tables_host[0] = self._randperm
         self._table_slot = 0
-        # 32 KiB pageable H2D copy: torch stages it and waits for the stream, so the host tables may be rewritten right
-        # after.  It happens on ~10 % of prepare() calls; schedule_ahead() batches these uploads instead.
-        self._tables_dev[0].copy_(torch.from_numpy(self._tables_host))
+        self._tables_dev[0].copy_(self._tables_pin[k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._tables_pin_events[k] = ev
         self._two_mask = int(self._lib.ml2048_two_mask(self._randfloat.ctypes.data, self._two_prob))
 
     _TABLE_BYTES = 2 * RAND_ROWS * 16  # one slot of the table ring
