@@ -204,7 +204,7 @@ typedef struct {
     const int64_t *id_offset; /* or null: device scalar added to ids of this shard (exclusive scan over ranks) */
     int64_t *reset_count;  /* device scalar out: number of slots reset by this call */
     int64_t *reset_indices;/* [num_games] out, ascending slots (np.flatnonzero, :629), or null */
-    int32_t *scratch;      /* [ml2048_prepare_scratch_ints(num_games)], zero-initialised by the caller once */
+    int32_t *scratch;      /* [ml2048_prepare_scratch_ints(num_games)] */
 
     /* device-resident schedule (or null), see ml2048_sched_entry; prepare never advances the cursor */
     const ml2048_sched_entry *sched;

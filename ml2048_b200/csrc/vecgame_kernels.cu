@@ -399,17 +399,27 @@ __device__ __forceinline__ int block_sum_256(int v, int *smem8)
     return t;
 }
 
-// Exclusive scan of the tile counts by ONE block of kThreads threads (in place), then the id bookkeeping.
-// scratch layout: [0, tiles) tile counts -> exclusive offsets; then (8-byte aligned) int64 id_base, int32 done-ticket
-template <int kThreads>
-__device__ __forceinline__ void scan_tiles(int32_t *tile_counts, int tiles, int64_t *id_base_slot, int64_t *game_count, int advance,
-                                           int64_t *reset_count, int *warp_tot, int *carry_s)
+__global__ void __launch_bounds__(kPrepThreads) prepare_count_kernel(const uint4 *term16, int64_t n16, int32_t *tile_counts)
 {
-    if (threadIdx.x == 0) *carry_s = 0;
+    __shared__ int warp_sums[kPrepThreads / 32];
+    const int64_t i = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x;
+    int c = 0;
+    if (i < n16) c = __popc(flags16(term16[i]));
+    const int total = block_sum_256(c, warp_sums);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+// scratch layout: [0, tiles) tile counts -> exclusive offsets; then (8-byte aligned) int64 id_base
+__global__ void __launch_bounds__(1024) prepare_scan_kernel(int32_t *tile_counts, int tiles, int64_t *id_base_slot,
+                                                            int64_t *game_count, int advance, int64_t *reset_count)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < tiles; base += kThreads) {
+    for (int base = 0; base < tiles; base += 1024) {
         const int i = base + threadIdx.x;
-        const int v = (i < tiles) ? reinterpret_cast<volatile int32_t *>(tile_counts)[i] : 0;  // written by other blocks
+        const int v = (i < tiles) ? tile_counts[i] : 0;
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -420,45 +430,19 @@ __device__ __forceinline__ void scan_tiles(int32_t *tile_counts, int tiles, int6
         __syncthreads();
         int wbase = 0;
         for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += warp_tot[w];
-        const int carry = *carry_s;
+        const int carry = carry_s;
         if (i < tiles) tile_counts[i] = carry + wbase + inc - v;
         __syncthreads();
-        if (threadIdx.x == kThreads - 1) *carry_s = carry + wbase + inc;
+        if (threadIdx.x == 1023) carry_s = carry + wbase + inc;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const int64_t total = *carry_s;
+        const int64_t total = carry_s;
         const int64_t base = *game_count;
         *id_base_slot = base;
         if (advance) *game_count = base + total;
         *reset_count = total;
     }
-}
-
-// Pass 1 + 2 in one launch: every block counts the finished games of its tile; the block that finishes LAST (a ticket
-// from one atomic counter, after a device-wide fence) sees all counts and scans them.  No block ever waits for another.
-__global__ void __launch_bounds__(kPrepThreads) prepare_count_scan_kernel(const uint4 *term16, int64_t n16, int32_t *tile_counts,
-                                                                          int tiles, int64_t *id_base_slot, int32_t *done_ticket,
-                                                                          int64_t *game_count, int advance, int64_t *reset_count)
-{
-    __shared__ int warp_sums[kPrepThreads / 32];
-    __shared__ int carry_s;
-    __shared__ int is_last;
-    const int64_t i = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x;
-    int c = 0;
-    if (i < n16) c = __popc(flags16(term16[i]));
-    const int total = block_sum_256(c, warp_sums);
-    if (threadIdx.x == 0) {
-        tile_counts[blockIdx.x] = total;
-        __threadfence();  // the count must be visible device-wide before the ticket is taken
-        const int ticket = atomicAdd(done_ticket, 1);
-        is_last = (ticket == (int)gridDim.x - 1);
-        if (is_last) *done_ticket = 0;  // ready for the next launch (stream-ordered)
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();  // acquire side: the other blocks' counts
-    scan_tiles<kPrepThreads>(tile_counts, tiles, id_base_slot, game_count, advance, reset_count, warp_sums, &carry_s);
 }
 
 // Reset pass over one tile of 4096 slots by one block.  `tile_offset` = finished games in earlier tiles, `id_base` = id of
@@ -772,7 +756,7 @@ int64_t ml2048_prepare_scratch_ints(int64_t num_games)
 {
     if (num_games <= 0) return 0;
     const int64_t tiles = (num_games + kPrepTile - 1) / kPrepTile;
-    return ((tiles + 1) / 2) * 2 + 4;  // tile counts (padded to 8 bytes) + one int64 (id base) + the done-ticket (zeroed by the caller once)
+    return ((tiles + 1) / 2) * 2 + 2;  // tile counts (padded to 8 bytes) + one int64
 }
 
 int ml2048_step(const ml2048_step_args *args, void *stream)
@@ -858,10 +842,9 @@ int ml2048_prepare_count(const ml2048_prepare_args *args, void *stream)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int64_t n16 = (a.num_games + 15) / 16;
     const int tiles = (int)((a.num_games + kPrepTile - 1) / kPrepTile);
-    int64_t *id_base_slot = prepare_id_base_slot(a, tiles);
-    prepare_count_scan_kernel<<<tiles, kPrepThreads, 0, s>>>(reinterpret_cast<const uint4 *>(a.terminated), n16, a.scratch, tiles,
-                                                            id_base_slot, reinterpret_cast<int32_t *>(id_base_slot + 1), a.game_count,
-                                                            a.id_offset ? 0 : 1, a.reset_count);
+    prepare_count_kernel<<<tiles, kPrepThreads, 0, s>>>(reinterpret_cast<const uint4 *>(a.terminated), n16, a.scratch);
+    prepare_scan_kernel<<<1, 1024, 0, s>>>(a.scratch, tiles, prepare_id_base_slot(a, tiles), a.game_count, a.id_offset ? 0 : 1,
+                                           a.reset_count);
     return launch_status();
 }
 

@@ -70,8 +70,8 @@ def test_argument_errors_without_gpu(lib):
     a.num_games = 8
     assert lib.ml2048_step(ctypes.byref(a), None) == -1  # null boards
     assert lib.ml2048_prepare_scratch_ints(0) == 0
-    assert lib.ml2048_prepare_scratch_ints(4096) == 6
-    assert lib.ml2048_prepare_scratch_ints(4097) == 6
+    assert lib.ml2048_prepare_scratch_ints(4096) == 4
+    assert lib.ml2048_prepare_scratch_ints(4097) == 4
 
 
 def test_two_mask_uses_double_compare(lib):
