@@ -213,19 +213,22 @@ ML2048_FN void move_board(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3
 ML2048_FN uint32_t valid_mask(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
 {
     const uint32_t n0 = occupied_flags(r0), n1 = occupied_flags(r1), n2 = occupied_flags(r2), n3 = occupied_flags(r3);
-    // rows: byte j+1 occupied and byte j empty -> can slide left; byte j-1 occupied and byte j empty -> right
-    const uint32_t left = ((n0 >> 8) & ~n0) | ((n1 >> 8) & ~n1) | ((n2 >> 8) & ~n2) | ((n3 >> 8) & ~n3);
-    const uint32_t right = ((n0 << 8) & ~n0) | ((n1 << 8) & ~n1) | ((n2 << 8) & ~n2) | ((n3 << 8) & ~n3);
-    // columns: row i+1 occupied above an empty row i -> up; the other way -> down
-    const uint32_t up = (n1 & ~n0) | (n2 & ~n1) | (n3 & ~n2);
-    const uint32_t down = (n0 & ~n1) | (n1 & ~n2) | (n2 & ~n3);
+    // slides on the 16-bit occupancy mask (bit 4*row+col; the gathers are multiplies, i.e. FMA-pipe work):
+    // a tile at col j+1 next to an empty col j can slide left, and so on
+    const uint32_t m = 0x00204081u;  // gathers bits 7,15,23,31 of a flag word into the top nibble
+    const uint32_t occ = ((n0 * m) >> 28) | (((n1 * m) >> 24) & 0xf0u) | (((n2 * m) >> 20) & 0xf00u) | (((n3 * m) >> 16) & 0xf000u);
+    const uint32_t emp = ~occ;
+    const bool left = ((occ >> 1) & emp & 0x7777u) != 0u;
+    const bool right = ((occ << 1) & emp & 0xeeeeu) != 0u;
+    const bool up = ((occ >> 4) & emp & 0x0fffu) != 0u;
+    const bool down = ((occ << 4) & emp & 0xfff0u) != 0u;
     // fusions: xor of neighbours is zero where the first one is a tile (byte 3 of a row xor is the cell itself)
     const uint32_t hfuse = (~add_on_fma_pipe(r0 ^ (r0 >> 8), kLo7) & n0) | (~add_on_fma_pipe(r1 ^ (r1 >> 8), kLo7) & n1) |
                            (~add_on_fma_pipe(r2 ^ (r2 >> 8), kLo7) & n2) | (~add_on_fma_pipe(r3 ^ (r3 >> 8), kLo7) & n3);
     const uint32_t vfuse = (~add_on_fma_pipe(r0 ^ r1, kLo7) & n0) | (~add_on_fma_pipe(r1 ^ r2, kLo7) & n1) |
                            (~add_on_fma_pipe(r2 ^ r3, kLo7) & n2);
-    const uint32_t l = ((left | hfuse) & kHi) != 0u, r = ((right | hfuse) & kHi) != 0u;
-    const uint32_t u = ((up | vfuse) & kHi) != 0u, d = ((down | vfuse) & kHi) != 0u;
+    const bool hf = (hfuse & kHi) != 0u, vf = (vfuse & kHi) != 0u;
+    const uint32_t l = left || hf, r = right || hf, u = up || vf, d = down || vf;
     return (l + r * 0x100u) + (u * 0x10000u + d * 0x1000000u);  // disjoint bytes: adds (IMAD) instead of shifts + ORs
 }
 

@@ -194,9 +194,11 @@ __device__ __forceinline__ void write_onehot_warp_dyn(int dtype, uint4 board, vo
 __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, int64_t g)
 {
     if (dtype == ML2048_ACT_U8) return reinterpret_cast<const uint8_t *>(actions)[g];
-    if (dtype == ML2048_ACT_I32) return (uint32_t) reinterpret_cast<const int32_t *>(actions)[g];
-    const long long a = reinterpret_cast<const long long *>(actions)[g];
-    return (a < 0 || a > 3) ? 4u : (uint32_t)a;
+    if (dtype == ML2048_ACT_I64) {
+        const unsigned long long a = reinterpret_cast<const unsigned long long *>(actions)[g];
+        return a > 3ull ? 4u : (uint32_t)a;  // negative values are huge as unsigned: invalid, like any value above 3
+    }
+    return (uint32_t) reinterpret_cast<const int32_t *>(actions)[g];
 }
 
 // Replaces _vec_step (game_numba.py:701-738) + the prev copies of VecGame.step (:672-673).
