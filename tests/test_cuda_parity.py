@@ -596,3 +596,29 @@ def test_rand_step_wraps_at_table_size(ml, oracle, scheduled):
     got = record_rollout(env, n, actions=want["actions"], full=True)
     compare_rollouts(got, want)
     assert ref._rand_step < 20 and env._rand_step == ref._rand_step
+
+
+def test_long_soak_against_oracle(ml, oracle):
+    """3000 runner steps (hundreds of table refreshes, ~28 finished episodes per slot) in lock step with the oracle;
+    every field compared every 250 steps and at the end."""
+    m, n = 20000, 3000
+    ref = oracle.OracleVecGame(m, "improved")
+    ref.reset(77)
+    env = _make(ml, m, "improved", output="torch")
+    env.reset(77)
+    acts = np.empty(m, np.int64)
+    for t in range(n):
+        (i0,) = ref.prepare()
+        (i1,) = env.prepare()
+        assert i1.numel() == i0.size
+        ref.random_valid_actions(t, acts)
+        ref.step(acts)
+        env.step(torch.from_numpy(acts).cuda())
+        if t % 250 == 249 or t == n - 1:
+            d = ref._data
+            for name, dev in (("board", env.observations()[0]), ("valid_actions", env.observations()[1]), ("step", env._step),
+                              ("id", env._id), ("terminated", env._terminated), ("invalid", env._invalid), ("merged", env._merged)):
+                np.testing.assert_array_equal(dev.cpu().numpy(), d[name], err_msg=f"{name} at step {t}")
+            for name, dev in (("score", env._score), ("reward", env._reward)):
+                np.testing.assert_array_equal(dev.cpu().numpy().view(np.uint32), d[name].view(np.uint32), err_msg=f"{name} at step {t}")
+    assert env._game_count == ref._game_count > 25 * m
