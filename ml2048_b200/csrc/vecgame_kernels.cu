@@ -719,7 +719,13 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
 #define ML2048_LAUNCH(OH)                                                                              \
     if (big) {                                                                                         \
         const int smem = kTmaStages * kTmaChunkBytes;                                                  \
-        cudaFuncSetAttribute(step_kernel<kRng, kLog, OH, kFull, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        static bool opted_in = false; /* > 48 KiB of dynamic shared memory needs a one-time opt-in per kernel */ \
+        if (!opted_in) {                                                                               \
+            const cudaError_t e = cudaFuncSetAttribute(step_kernel<kRng, kLog, OH, kFull, T>,           \
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+            if (e != cudaSuccess) return (int)e;                                                       \
+            opted_in = true;                                                                           \
+        }                                                                                              \
         step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, smem, s>>>(a);                             \
     } else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
 #else
@@ -889,16 +895,14 @@ int ml2048_reset_state(void *board_a, void *board_b, void *valid_a, void *valid_
         return ML2048_E_NULL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)num_games;
-    cudaMemsetAsync(board_a, 0, n * 16, s);
-    cudaMemsetAsync(board_b, 0, n * 16, s);
-    cudaMemsetAsync(valid_a, 0, n * 4, s);
-    cudaMemsetAsync(valid_b, 0, n * 4, s);
-    cudaMemsetAsync(id, 0, n * 4, s);
-    cudaMemsetAsync(step, 0, n * 4, s);
-    cudaMemsetAsync(score, 0, n * 4, s);
-    cudaMemsetAsync(reward, 0, n * 4, s);
-    cudaMemsetAsync(invalid, 0, n, s);
-    if (merged) cudaMemsetAsync(merged, 0, n * 16, s);
+    const struct { void *p; size_t bytes; } clears[] = {{board_a, n * 16}, {board_b, n * 16}, {valid_a, n * 4}, {valid_b, n * 4},
+                                                        {id, n * 4},       {step, n * 4},     {score, n * 4},   {reward, n * 4},
+                                                        {invalid, n},      {merged, n * 16}};
+    for (const auto &c : clears) {
+        if (!c.p) continue;
+        const cudaError_t e = cudaMemsetAsync(c.p, 0, c.bytes, s);
+        if (e != cudaSuccess) return (int)e;
+    }
     const int64_t padded = (num_games + 15) / 16 * 16;
     fill_terminated_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, s>>>(terminated, num_games, padded);
     return launch_status();
