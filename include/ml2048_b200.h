@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ML2048_ABI_VERSION 6
+#define ML2048_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define ML2048_API __attribute__((visibility("default")))
@@ -168,6 +168,19 @@ typedef struct {
     uint8_t *tr_next_valid_actions;/* [num_games][4] */
     int32_t *tr_step;              /* [num_games] */
     uint8_t *tr_terminated;        /* [num_games] (bool bytes) */
+
+    /* Whole-episode capture keyed by GAME ID (or null), the device form of ReplayRecorder (replay.py:110-232): every
+     * runner step of a game with id in [traj_id_base, traj_id_base + traj_capacity) appends the row
+     * (prev_state, action, score) -- invalid moves included, like replay.py:178-189 -- and the step that finishes the game
+     * appends a last row (final state, 0, score) (:191-201).  Rows beyond traj_max_rows are dropped (the count saturates). */
+    int32_t *age;                  /* [num_games]: runner steps since the slot's game started; cleared by ml2048_prepare */
+    int64_t traj_id_base;
+    int64_t traj_capacity;
+    int64_t traj_max_rows;
+    int8_t *traj_state;            /* [traj_capacity][traj_max_rows][16] */
+    int8_t *traj_action;           /* [traj_capacity][traj_max_rows] */
+    float *traj_score;             /* [traj_capacity][traj_max_rows] */
+    int32_t *traj_rows;            /* [traj_capacity]: rows written (= steps + 1 once the game is over) */
 } ml2048_step_args;
 
 /* Arguments of the auto-reset.  Replaces the host loop of VecGame.prepare (game_numba.py:629-658):
@@ -210,6 +223,7 @@ typedef struct {
     const ml2048_sched_entry *sched;
     const int64_t *sched_cursor;
     int64_t table_stride;  /* bytes between consecutive slots of the table ring (randperm = slot 0) */
+    int32_t *age;          /* [num_games] or null: cleared for every reset slot (see ml2048_step_args.age) */
 } ml2048_prepare_args;
 
 /* ---- entry points ---------------------------------------------------------------------------- */

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libml2048_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 STATS_REPLICAS = 64
 STATS_WORDS = 24  # 20 histogram bins + episodes, score_sum, step_sum, score_max (unsigned long long each)
 
@@ -77,6 +77,14 @@ class StepArgs(C.Structure):
         ("tr_next_valid_actions", C.c_void_p),
         ("tr_step", C.c_void_p),
         ("tr_terminated", C.c_void_p),
+        ("age", C.c_void_p),
+        ("traj_id_base", C.c_int64),
+        ("traj_capacity", C.c_int64),
+        ("traj_max_rows", C.c_int64),
+        ("traj_state", C.c_void_p),
+        ("traj_action", C.c_void_p),
+        ("traj_score", C.c_void_p),
+        ("traj_rows", C.c_void_p),
     ]
 
 
@@ -114,6 +122,7 @@ class PrepareArgs(C.Structure):
         ("sched", C.c_void_p),
         ("sched_cursor", C.c_void_p),
         ("table_stride", C.c_int64),
+        ("age", C.c_void_p),
     ]
 
 

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
 
         uint32_t r0 = bd.x, r1 = bd.y, r2 = bd.z, r3 = bd.w;
         Fusions f;
-        float tr_reward = 0.0f;
+        float tr_reward = 0.0f, tr_score = 0.0f;
         int32_t tr_step = 0;
         uint32_t tr_term = 0u, tr_mask = 0u;
         move_board(r0, r1, r2, r3, action & 3u, f);
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
                 fusion_log(f, m0, m1, m2, m3);
                 reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(m0, m1, m2, m3);
             }
-            tr_reward = reward, tr_step = nstep, tr_term = dead ? 1 : 0, tr_mask = vm;
+            tr_reward = reward, tr_score = score, tr_step = nstep, tr_term = dead ? 1 : 0, tr_mask = vm;
             if (kFull && dead && a.episode_max_tile) {
                 // eval_perf.py semantics: episodes are keyed by game id, not by finishing order
                 const int64_t e = (int64_t)a.id[g] - a.episode_id_base;
@@ -351,6 +351,31 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
         }
         out_board = make_uint4(r0, r1, r2, r3);
         reinterpret_cast<uint4 *>(a.board_out)[g] = out_board;
+        if (kFull && a.traj_state) {
+            // ReplayRecorder on the device (replay.py:161-201): one row per runner step of a recorded game
+            const int32_t row = a.age[g];
+            const bool was_over = !moved && a.terminated[g];  // finished games idle until prepare(): not recorded again
+            const int64_t e = (int64_t)a.id[g] - a.traj_id_base;
+            if (!was_over && e >= 0 && e < a.traj_capacity) {
+                const bool dead_now = moved && tr_term;
+                const float sc = moved ? tr_score : a.score[g];  // after this step (stale on an invalid move, like result["score"])
+                if (row < a.traj_max_rows) {
+                    const int64_t k = e * a.traj_max_rows + row;
+                    reinterpret_cast<uint4 *>(a.traj_state)[k] = bd;
+                    a.traj_action[k] = (int8_t)action;
+                    a.traj_score[k] = sc;
+                }
+                if (dead_now && row + 1 < a.traj_max_rows) {
+                    const int64_t k = e * a.traj_max_rows + row + 1;
+                    reinterpret_cast<uint4 *>(a.traj_state)[k] = out_board;
+                    a.traj_action[k] = 0;
+                    a.traj_score[k] = sc;
+                }
+                const int64_t rows = (int64_t)row + 1 + (dead_now ? 1 : 0);
+                a.traj_rows[e] = (int32_t)(rows < a.traj_max_rows ? rows : a.traj_max_rows);
+            }
+            if (!was_over) a.age[g] = row + 1;
+        }
         if (kFull) {  // transition record (REPLAY_SPEC row, replay.py:10-20)
             if (a.tr_state) reinterpret_cast<uint4 *>(a.tr_state)[g] = bd;
             if (a.tr_valid_actions)
@@ -530,6 +555,7 @@ __device__ __forceinline__ int apply_tile(const ml2048_prepare_args &a, int64_t 
         a.reward[g] = 0.0f;
         a.invalid[g] = 0;
         if (a.merged) reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(0, 0, 0, 0);
+        if (a.age) a.age[g] = 0;
         if (a.reset_indices) a.reset_indices[order] = g;
         order += 1;
         }
@@ -746,7 +772,7 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
 template <int kRng>
 int launch_step(const ml2048_step_args &a, cudaStream_t s)
 {
-    const bool full = a.action_mode == ML2048_ACTIONS_FROM_LOGITS || a.episode_max_tile || a.tr_state || a.tr_valid_actions ||
+    const bool full = a.action_mode == ML2048_ACTIONS_FROM_LOGITS || a.episode_max_tile || a.traj_state || a.tr_state || a.tr_valid_actions ||
                       a.tr_action || a.tr_reward || a.tr_next_state || a.tr_next_valid_actions || a.tr_step || a.tr_terminated;
     if (full) return a.merged ? launch_step_onehot<kRng, true, true>(a, s) : launch_step_onehot<kRng, false, true>(a, s);
     return a.merged ? launch_step_onehot<kRng, true, false>(a, s) : launch_step_onehot<kRng, false, false>(a, s);
@@ -799,6 +825,10 @@ int ml2048_step(const ml2048_step_args *args, void *stream)
         return ML2048_E_ALIGN;
     if (a.onehot_out && (a.onehot_dtype < ML2048_ONEHOT_F32 || a.onehot_dtype > ML2048_ONEHOT_U8)) return ML2048_E_ENUM;
     if (a.episode_max_tile && (!a.id || !a.episode_steps || !a.episode_score || a.episode_capacity <= 0)) return ML2048_E_NULL;
+    if (a.traj_state && (!a.id || !a.age || !a.traj_action || !a.traj_score || !a.traj_rows || a.traj_capacity <= 0 || a.traj_max_rows <= 0))
+        return ML2048_E_NULL;
+    if (misaligned(a.traj_state, 16) || misaligned(a.traj_score, 4) || misaligned(a.traj_rows, 4) || misaligned(a.age, 4))
+        return ML2048_E_ALIGN;
     if (a.sched) {
         if (!a.sched_cursor || a.sched_cursor == a.sched_cursor_next) return ML2048_E_NULL;
         if (misaligned(a.sched, 8) || misaligned(a.sched_cursor, 8) || misaligned(a.sched_cursor_next, 8) || (a.table_stride & 15))

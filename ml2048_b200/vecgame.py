@@ -872,6 +872,8 @@ class VecGame:
                     a.onehot_out = self._onehot.data_ptr() + lo * 256 * self._onehot.element_size()
                 if self._step_args.id:
                     a.id = self._id.data_ptr() + 4 * lo
+                if self._step_args.age:
+                    a.age = self._age.data_ptr() + 4 * lo
                 _lib.check(self._lib.ml2048_step(C.byref(a), raw_main), "ml2048_step")
                 d2h.wait_stream(main)
                 with torch.cuda.stream(d2h):
@@ -985,6 +987,36 @@ class VecGame:
         a.episode_steps = self._p(self._ep_steps)
         a.episode_score = self._p(self._ep_score)
         a.episode_max_tile = self._p(self._ep_max_tile)
+
+    def enable_trajectory_log(self, capacity: int, max_rows: int = 4096, id_base: int = 0) -> None:
+        """Capture whole episodes of the games with id in [id_base, id_base+capacity) on the device: one row
+        (prev_state, action, score) per runner step plus the final (state, 0, score) row, like ``ReplayRecorder``
+        (replay.py:161-201) but inside the step kernel.  ``max_rows`` bounds the rows kept per game."""
+        if capacity <= 0 or max_rows <= 1:
+            raise ValueError((capacity, max_rows))
+        dev = self.device
+        self._age = torch.zeros((self._size,), dtype=torch.int32, device=dev)
+        self._traj_state = torch.zeros((capacity, max_rows, 16), dtype=torch.int8, device=dev)
+        self._traj_action = torch.zeros((capacity, max_rows), dtype=torch.int8, device=dev)
+        self._traj_score = torch.zeros((capacity, max_rows), dtype=torch.float32, device=dev)
+        self._traj_rows = torch.zeros((capacity,), dtype=torch.int32, device=dev)
+        a = self._step_args
+        a.id = self._p(self._id)
+        a.age = self._p(self._age)
+        a.traj_id_base, a.traj_capacity, a.traj_max_rows = int(id_base), int(capacity), int(max_rows)
+        a.traj_state = self._p(self._traj_state)
+        a.traj_action = self._p(self._traj_action)
+        a.traj_score = self._p(self._traj_score)
+        a.traj_rows = self._p(self._traj_rows)
+        self._prep_args.age = self._p(self._age)
+
+    def trajectory(self, index: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(state (rows,16) int8, action (rows,) int8, score (rows,) f32) of game id ``id_base + index`` so far --
+        ``RecordBuffer.contiguous_result()`` (replay.py:86-107): rows = steps + 1 once the game is over."""
+        if getattr(self, "_traj_rows", None) is None:
+            raise RuntimeError("call enable_trajectory_log(capacity) first")
+        rows = int(self._traj_rows[index].item())
+        return self._traj_state[index, :rows], self._traj_action[index, :rows], self._traj_score[index, :rows]
 
     def episode_log(self) -> dict[str, torch.Tensor]:
         """Device tensors indexed by (game id - id_base): ``steps`` i32, ``score`` f32, ``max_tile`` u8 (0 = unfinished)."""

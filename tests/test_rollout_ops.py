@@ -229,3 +229,46 @@ def test_whole_rollout_with_policy_as_one_cuda_graph(ml):
         assert torch.allclose(buf_g["action_log_prob"], buf_e["action_log_prob"], atol=1e-6)
     assert torch.equal(graphed.observations()[0], eager.observations()[0])
     assert graphed._game_count == eager._game_count
+
+
+def test_trajectory_log_matches_replay_recorder(ml, oracle):
+    """Device episode capture == ReplayRecorder's bookkeeping (replay.py:161-201) replayed on the host from the oracle's
+    results: one (prev_state, action, score) row per runner step (invalid moves included), a final (state, 0, score) row."""
+    from oracle.rollout import pick_actions
+
+    m, n, cap, max_rows = 400, 600, 700, 512
+    ref = oracle.OracleVecGame(m, "improved")
+    ref.reset(6)
+    env = ml.VecGame(m, ml.reward_fn_improved, output="torch")
+    env.reset(6)
+    env.enable_trajectory_log(cap, max_rows)
+    rng = np.random.default_rng(2)
+    rows = {}        # game id -> list of (state, action, score)
+    finished = set()
+    for t in range(n):
+        ref.prepare()
+        env.prepare()
+        ids = ref._data["id"].copy()
+        acts = pick_actions(ref.observations()[1], rng, wild=0.08)
+        was_over = ref._data["terminated"].astype(bool).copy()
+        res = ref.step(acts)
+        env.step(torch.from_numpy(acts).cuda())
+        for slot in range(m):
+            gid = int(ids[slot])
+            if gid >= cap or was_over[slot] or gid in finished:
+                continue
+            rows.setdefault(gid, []).append((res["prev_state"][slot].copy(), int(acts[slot]), float(res["score"][slot])))
+            if res["terminated"][slot] and not res["invalid"][slot]:
+                rows[gid].append((res["state"][slot].copy(), 0, float(res["score"][slot])))
+                finished.add(gid)
+    assert len(finished) > 300
+    checked = 0
+    for gid, want in rows.items():
+        state, action, score = env.trajectory(gid)
+        k = min(len(want), max_rows)
+        assert state.shape[0] == k, (gid, state.shape[0], len(want))
+        np.testing.assert_array_equal(state.cpu().numpy(), np.stack([w[0] for w in want[:k]]).astype(np.int8))
+        np.testing.assert_array_equal(action.cpu().numpy(), np.array([w[1] for w in want[:k]], np.int8))
+        np.testing.assert_array_equal(score.cpu().numpy(), np.array([w[2] for w in want[:k]], np.float32))
+        checked += 1
+    assert checked >= cap - 5
