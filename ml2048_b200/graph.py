@@ -36,7 +36,10 @@ class GraphedRollout:
         env.configure(sync_free=True)
         if env._sched_len and env._sched_pos < env._sched_len:
             raise RuntimeError("the environment already has a pending device schedule")
-        env.schedule_ahead(self.window, min_steps=self.steps)
+        # min_steps = window reserves one table slot per step, so a window is never cut short by table refreshes and
+        # always holds a whole number of replays
+        self.window -= self.window % self.steps
+        env.schedule_ahead(self.window, min_steps=self.window)
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=env.device)
         side.wait_stream(torch.cuda.current_stream(env.device))
@@ -72,11 +75,8 @@ class GraphedRollout:
         env = self.env
         for _ in range(times):
             if env._sched_pos + self.steps > env._sched_len:
-                if env._sched_pos < env._sched_len:
-                    # a partial tail cannot feed a whole replay: run it eagerly, then refill
-                    while env._sched_pos < env._sched_len:
-                        env.prepare()
-                        env.step_random()
-                env.schedule_ahead(self.window, min_steps=self.steps)
+                if env._sched_pos != env._sched_len:
+                    raise RuntimeError("the device schedule was consumed outside this GraphedRollout")
+                env.schedule_ahead(self.window, min_steps=self.window)
             self.graph.replay()
             env._sched_pos += self.steps

@@ -460,7 +460,9 @@ class VecGame:
         if slots > self._table_slots:
             self._table_slots = slots
             self._tables_dev = torch.zeros((slots, 2, RAND_ROWS, 16), dtype=torch.uint8, device=self.device)
-        ring = np.zeros((slots, 2, RAND_ROWS, 16), dtype=np.uint8)
+        ring = getattr(self, "_ring_host", None)
+        if ring is None or ring.shape[0] < slots:
+            ring = self._ring_host = np.zeros((slots, 2, RAND_ROWS, 16), dtype=np.uint8)
 
         def put(slot: int) -> None:
             ring[slot, 0] = self._randperm
