@@ -109,10 +109,11 @@ typedef struct {
 
     const void *board_in;  /* [num_games][16] u8 */
     void *board_out;       /* [num_games][16] u8, must not alias board_in */
-    const void *valid_in;  /* [num_games][4] u8; only read when action_mode == RANDOM_VALID, else may be null */
+    const void *valid_in;  /* [num_games][4] u8; read when action_mode is RANDOM_VALID or FROM_LOGITS or tr_valid_actions
+                              is set; may be null otherwise (the move itself decides validity) */
     void *valid_out;       /* [num_games][4] u8 */
     const void *actions;   /* [num_games] of action_dtype, values 0..3 (others count as invalid moves) */
-    void *actions_out;     /* [num_games] u8 or null (RANDOM_VALID only) */
+    void *actions_out;     /* [num_games] u8 or null: the action chosen in-kernel (RANDOM_VALID, FROM_LOGITS) */
 
     int32_t *step;         /* in place; += 1 on a valid move            (game_numba.py:719) */
     float *score;          /* in place; += normal reward on a valid move (:729-731) */
