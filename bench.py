@@ -514,6 +514,28 @@ def measure_extras(ml2048_b200, torch, dev, seed: int) -> dict:
             env.step_random()
         ms = timed(env, n, graph_steps)
         out[name] = {"us_per_step": ms * 1e3, "env_steps_per_s": m / (ms * 1e-3)}
+        if name == "core_only_replay_M2^24":
+            # the environment alone: actions GIVEN (recorded from this trajectory, device-resident), step kernel timed by itself
+            snap = env.state_dict()
+            k = 24
+            acts = torch.empty((k, m), dtype=torch.uint8, device=dev)
+            for t in range(k):
+                env.prepare()
+                env.step_random(return_actions=True)
+                acts[t].copy_(env.sampled_actions)
+            env.load_state_dict(snap)
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+            for t in range(k):
+                env.prepare()
+                ev[t][0].record()
+                env.step(acts[t])
+                ev[t][1].record()
+            torch.cuda.synchronize()
+            kms = sum(a.elapsed_time(b) for a, b in ev[4:]) / (k - 4)
+            out["core_only_given_actions_step_kernel_M2^24"] = {
+                "us_per_launch": kms * 1e3, "env_steps_per_s": m / (kms * 1e-3),
+                "hbm_frac": BYTES_CORE * m / (kms * 1e-3) / 1e9 / load_peaks()[0]}
+            del snap, acts
         del env
         torch.cuda.empty_cache()
     return out
