@@ -18,7 +18,9 @@ _ONEHOT = {torch.float32: _lib.ONEHOT_F32, torch.bfloat16: _lib.ONEHOT_BF16, tor
 
 
 def _stream(t: torch.Tensor) -> int:
-    return torch._C._cuda_getCurrentRawStream(t.device.index)
+    from .vecgame import _raw_stream
+
+    return _raw_stream(t.device.index)
 
 
 def _cuda(t: torch.Tensor, name: str) -> None:

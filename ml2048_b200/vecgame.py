@@ -37,6 +37,14 @@ from . import _lib
 from .host_rng import RAND_ROWS, make_schedule
 from .rewards import reward_kind
 
+try:  # the raw-handle accessor is private but ~10x cheaper than building a Stream object per call
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover - older/newer torch without it
+
+    def _raw_stream(index: int) -> int:
+        return torch.cuda.current_stream(index).cuda_stream
+
+
 _ONEHOT = {
     None: (_lib.ONEHOT_NONE, None),
     "f32": (_lib.ONEHOT_F32, torch.float32),
@@ -277,7 +285,7 @@ class VecGame:
         return None if t is None else t.data_ptr()
 
     def _stream(self) -> int:
-        return torch._C._cuda_getCurrentRawStream(self._dev_index)
+        return _raw_stream(self._dev_index)
 
     class _DeviceGuard:
         """Cheap `with torch.cuda.device(...)`: does nothing when the environment's device is already current."""
