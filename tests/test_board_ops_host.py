@@ -178,3 +178,38 @@ def test_philox_known_answers(shim):
         out = np.zeros(4, np.uint32)
         shim.hs_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data)
         assert tuple(int(x) for x in out) == want
+
+
+def test_hypothesis_boards_against_oracle(shim, oracle):
+    """Property-based: arbitrary boards (exponents 0..17, any density) x any direction: the product's SWAR move, mask,
+    max tile and fusion bookkeeping equal the oracle's scalar restatement of the reference."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    cells = st.lists(st.integers(min_value=0, max_value=17), min_size=16, max_size=16)
+
+    @settings(max_examples=3000, deadline=None)
+    @given(cells=cells, action=st.integers(min_value=0, max_value=3))
+    def check(cells, action):
+        board = np.array(cells, np.uint8)
+        out, gain, rank, count, merged, mask = _move_batch(shim, board[None, :], action)
+        want_board, want_merged18 = None, None
+        b = board.copy()
+        buckets = np.zeros(18, np.int64)
+        # oracle line by line (its single-board entry point only has 16 merged slots, as the reference)
+        lines = {0: [(4 * r, 1) for r in range(4)], 1: [(4 * r + 3, -1) for r in range(4)],
+                 2: [(c, 4) for c in range(4)], 3: [(12 + c, -4) for c in range(4)]}[action]
+        for first, stride in lines:
+            idx = [first + k * stride for k in range(4)]
+            pushed, bk = oracle.line_push(b[idx], False)
+            b[idx] = pushed
+            buckets += bk
+        np.testing.assert_array_equal(out[0], b)
+        assert int(gain[0]) == int(sum(int(buckets[k]) << (k + 1) for k in range(18)))
+        assert int(count[0]) == int(buckets.sum())
+        assert int(rank[0]) == int(sum((k + 1) * int(buckets[k]) for k in range(18)))
+        np.testing.assert_array_equal(merged[0], buckets[:16].astype(np.uint8))
+        np.testing.assert_array_equal(mask[0], oracle.board_valid(board))
+        assert shim.hs_max_cell(board.ctypes.data) == board.max()
+
+    check()
