@@ -363,6 +363,22 @@ class VecGame:
     # costs, so prepare() and step() mirror the WHOLE state arena to the host with one copy and one sync instead
     # of one copy + sync per field.  Large batches stay lazy: there the copies are PCIe-bandwidth bound.
     _EAGER_HOST_MAX_GAMES = 1 << 15
+    # Medium batches: still latency-sensitive, but mirroring everything would waste bandwidth: the fields the reference's
+    # callers read (runner.py:165, replay.py:170-173, run_train3.py:138-149) are copied together behind one synchronisation.
+    _BATCHED_HOST_MAX_GAMES = 1 << 20
+    _COMMON_FIELDS = ("state", "valid_actions", "prev_state", "prev_valid_actions", "reward", "score", "step", "terminated")
+
+    def _fetch_many(self, keys) -> dict[str, np.ndarray]:
+        """Several per-field D2H copies behind ONE synchronisation."""
+        stream = torch.cuda.current_stream(self.device)
+        bufs = {}
+        for k in keys:
+            t = self._device_field(k)
+            buf = self._pinned(k, t)
+            buf.copy_(t, non_blocking=True)
+            bufs[k] = buf
+        stream.synchronize()
+        return {k: b.numpy() for k, b in bufs.items()}
 
     def _mirror_to_host(self) -> dict[str, np.ndarray]:
         """One D2H copy of the state arena into its pinned host mirror; returns NumPy views of the mirror by name."""
@@ -600,6 +616,14 @@ class VecGame:
             views = self._mirror_to_host()
             self._obs_cache = (views["_board"][cur], views["_valid"][cur])
             return (views["_reset_indices_dev"][: int(views["_reset_count_dev"][0])].copy(),)
+        if self._output == "numpy" and self._size <= self._BATCHED_HOST_MAX_GAMES:
+            # the count and the post-reset observations behind one synchronisation; the index list only if non-empty
+            cnt = self._pinned("_reset_count", self._reset_count_dev)
+            cnt.copy_(self._reset_count_dev, non_blocking=True)
+            got = self._fetch_many(("state", "valid_actions"))
+            self._obs_cache = (got["state"], got["valid_actions"])
+            n = int(cnt[0])
+            return (self._reset_indices_dev[:n].cpu().numpy() if n else np.zeros((0,), dtype=np.int64),)
         n = int(self._reset_count_dev.item())
         idx = self._reset_indices_dev[:n]
         if self._output == "torch":
@@ -629,9 +653,10 @@ class VecGame:
         if fetch and not record and self._can_pipeline(actions):
             return self._step_pipelined(actions, tuple(fetch))
         a = self._step_args
-        eager_host = (self._output == "numpy" and self._size <= self._EAGER_HOST_MAX_GAMES and not self._sync_free
-                      and isinstance(actions, np.ndarray))
-        if eager_host:
+        host_actions = self._output == "numpy" and not self._sync_free and isinstance(actions, np.ndarray)
+        eager_host = host_actions and self._size <= self._EAGER_HOST_MAX_GAMES
+        batched_host = host_actions and not eager_host and self._size <= self._BATCHED_HOST_MAX_GAMES
+        if eager_host or batched_host:
             dev_actions, a.action_dtype = self._stage_actions_pinned(actions)
         else:
             dev_actions, a.action_dtype = self._stage_actions(actions)
@@ -648,6 +673,9 @@ class VecGame:
             for k in VecStepResult.KEYS:
                 if k != "merged" or self._merged is not None:
                     dict.__setitem__(res, k, self._mirror_field(views, k))
+        elif batched_host:
+            for k, v in self._fetch_many(self._COMMON_FIELDS).items():
+                dict.__setitem__(res, k, v)  # merged / invalid stay lazy
         return res
 
     def _stage_actions_pinned(self, actions: np.ndarray) -> tuple[torch.Tensor, int]:
