@@ -15,6 +15,7 @@ What is produced (all from the reference's own functions, reference: src/ml2048/
   boards.npz           random boards x 4 actions: moved board, merged, mask, the four rewards
   rollout_*.npz        lock-step rollouts through VecGame (prepare/observations/step), every
                        VecStepResult field + ids + reset indices (full or CRC32 digests)
+  runner_stack.npz     the reference's VecRunner + RunnerStats + ReplayRecorder driven by a deterministic policy
   gae.npz              compute_gae (gae.py:7-68) on random fp32 inputs with a stand-in critic
   schedule_*.npz       the host random draws of one rollout recorded from the reference's generator
                        (tables at every refresh, coins, offsets): input of the "replay" mode
@@ -243,12 +244,69 @@ def gen_gae() -> None:
     np.savez_compressed(os.path.join(OUT_DIR, "gae.npz"), **out)
 
 
+def gen_runner() -> None:
+    """The reference's OWN rollout stack -- VecRunner + RunnerStats + ReplayRecorder (runner.py, replay.py) -- driven by
+    a deterministic policy, so that the device-side runner / statistics / episode log / trajectory capture can be held
+    to the reference's code rather than to a restatement of it."""
+    import torch
+    from ml2048.policy import Policy
+    from ml2048.replay import ReplayRecorder
+    from ml2048.runner import RunnerStats, VecRunner
+
+    class CyclingPolicy(Policy):
+        """k-th valid action with k = (7 t + 13 slot) mod nvalid; action 0 when nothing is valid."""
+
+        def __init__(self):
+            super().__init__()
+            self.t = 0
+
+        def sample_actions(self, state, valid_actions, *, generator=None):
+            m = valid_actions.shape[0]
+            nvalid = valid_actions.sum(dim=1)
+            k = (7 * self.t + 13 * torch.arange(m)) % nvalid.clamp(min=1)
+            rank = torch.cumsum(valid_actions.long(), dim=1) - 1
+            hit = valid_actions & (rank == k[:, None])
+            actions = torch.where(nvalid > 0, hit.long().argmax(dim=1), torch.zeros(m, dtype=torch.long))
+            self.t += 1
+            return actions, torch.zeros(m)
+
+    m, steps, seed = 384, 900, 11
+    vg = ref.VecGame(m, ref.reward_fn_improved)
+    vg.reset(seed)
+    runner = VecRunner(vg, 16, sample_device="cpu")
+    stats = RunnerStats()
+    rec = ReplayRecorder(10**9, 10**9, segment_size=64)
+    runner.add_callback(VecRunner.EVENT_PREPARED, rec.on_prepared)
+    runner.add_callback(VecRunner.EVENT_STEPPED, rec.on_stepped)
+    runner.add_callback(VecRunner.EVENT_STEPPED, stats.on_stepped)
+    runner.step_many(CyclingPolicy(), steps)
+    bufs = sorted(rec.ready_buffers, key=lambda b: b.id)
+    out = {
+        "meta": np.array([m, steps, seed], np.int64),
+        "stats_counts": stats.counts.astype(np.int64),
+        "stats_terminated": np.array(int(stats.terminated_count), np.int64),
+        "summary_live": np.array([[a, b] for a, b, _ in vg.summary()], np.int64),
+        "buf_id": np.array([b.id for b in bufs], np.int64),
+        "buf_steps": np.array([b.steps for b in bufs], np.int64),
+        "buf_maxcell": np.array([b.maxcell for b in bufs], np.int64),
+        "buf_score": np.array([b.score for b in bufs], np.float32),
+        "game_count": np.array(vg._game_count, np.int64),
+    }
+    keep = [b for b in bufs if b.id in (0, 1, 100, 383, 384, 500, 1000)]
+    for b in keep:
+        st, ac, sc = b.contiguous_result()
+        out[f"traj_{b.id}_state"], out[f"traj_{b.id}_action"], out[f"traj_{b.id}_score"] = st, ac, sc
+    out["traj_ids"] = np.array([b.id for b in keep], np.int64)
+    np.savez_compressed(os.path.join(OUT_DIR, "runner_stack.npz"), **out)
+    print(f"runner stack: {len(bufs)} finished recorded games, terminated_count={int(stats.terminated_count)}")
+
+
 def main() -> None:
     os.makedirs(OUT_DIR, exist_ok=True)
     print("numba", numba.__version__, "numpy", np.__version__)
     only = set(sys.argv[1:])
     for name, fn in (("kat", gen_kat), ("lines", gen_line_table), ("boards", gen_boards), ("rollouts", gen_rollouts),
-                     ("schedules", gen_schedules), ("gae", gen_gae)):
+                     ("schedules", gen_schedules), ("gae", gen_gae), ("runner", gen_runner)):
         if not only or name in only:
             fn()
     with open(os.path.join(OUT_DIR, "PROVENANCE.txt"), "w") as fh:

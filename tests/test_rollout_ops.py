@@ -272,3 +272,55 @@ def test_trajectory_log_matches_replay_recorder(ml, oracle):
         np.testing.assert_array_equal(score.cpu().numpy(), np.array([w[2] for w in want[:k]], np.float32))
         checked += 1
     assert checked >= cap - 5
+
+
+class _CyclingPolicy:
+    """The deterministic policy of oracle/gen_golden.py::gen_runner, on the device."""
+
+    def __init__(self):
+        self.t = 0
+
+    def sample_actions(self, state, valid_actions, *, generator=None):
+        m = valid_actions.shape[0]
+        nvalid = valid_actions.sum(dim=1)
+        k = (7 * self.t + 13 * torch.arange(m, device=valid_actions.device)) % nvalid.clamp(min=1)
+        rank = torch.cumsum(valid_actions.long(), dim=1) - 1
+        hit = valid_actions & (rank == k[:, None])
+        actions = torch.where(nvalid > 0, hit.long().argmax(dim=1), torch.zeros(m, dtype=torch.long, device=valid_actions.device))
+        self.t += 1
+        return actions, torch.zeros(m, device=valid_actions.device)
+
+
+def test_device_runner_reproduces_the_reference_runner_stack(ml):
+    """tests/golden/runner_stack.npz was produced by the reference's OWN VecRunner + RunnerStats + ReplayRecorder
+    (runner.py, replay.py) around the reference VecGame.  The device runner with the same policy must give the same
+    terminated-game histogram, the same per-game-id records (steps, max tile, score) and the same trajectories."""
+    from ml2048_b200.runner import DeviceRunner, DeviceRunnerStats
+
+    g = golden("runner_stack.npz")
+    m, steps, seed = [int(x) for x in g["meta"]]
+    env = ml.VecGame(m, ml.reward_fn_improved, output="torch")
+    env.reset(seed)
+    cap = int(g["game_count"])
+    env.enable_episode_log(cap)
+    env.enable_trajectory_log(1001, 512)
+    runner = DeviceRunner(env, 16)
+    runner.step_many(_CyclingPolicy(), steps)
+    stats = DeviceRunnerStats(env)
+    np.testing.assert_array_equal(stats.counts, g["stats_counts"])          # RunnerStats.counts (runner.py:150-166)
+    assert stats.terminated_count == int(g["stats_terminated"])
+    assert env._game_count == cap
+    assert [(a, int(b)) for a, b, _ in env.summary()] == [tuple(r) for r in g["summary_live"].tolist()]
+    log = env.episode_log()
+    ids = torch.from_numpy(g["buf_id"]).cuda()
+    np.testing.assert_array_equal(log["steps"][ids].cpu().numpy(), g["buf_steps"])      # RecordBuffer.steps
+    np.testing.assert_array_equal(log["max_tile"][ids].cpu().numpy(), g["buf_maxcell"])  # RecordBuffer.maxcell
+    np.testing.assert_array_equal(log["score"][ids].cpu().numpy(), g["buf_score"])       # RecordBuffer.score
+    unfinished = torch.ones(cap, dtype=torch.bool, device="cuda")
+    unfinished[ids] = False
+    assert int(log["max_tile"][unfinished].sum()) == 0  # games the recorder had not finished are unfinished here too
+    for gid in g["traj_ids"].tolist():                  # RecordBuffer.contiguous_result (replay.py:86-107)
+        st, ac, sc = env.trajectory(gid)
+        np.testing.assert_array_equal(st.cpu().numpy(), g[f"traj_{gid}_state"])
+        np.testing.assert_array_equal(ac.cpu().numpy(), g[f"traj_{gid}_action"])
+        np.testing.assert_array_equal(sc.cpu().numpy(), g[f"traj_{gid}_score"])
