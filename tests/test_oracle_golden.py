@@ -136,3 +136,34 @@ def test_ctor_errors(oracle):
     env = oracle.OracleVecGame(4)
     with pytest.raises(AssertionError):
         env.step(np.zeros(5, np.int64))
+
+
+def test_runner_stats_fixture_from_the_reference_runner(oracle):
+    """RunnerStats of the reference's own VecRunner (tests/golden/runner_stack.npz) == the oracle's _update_count
+    restatement (orc_terminated_hist, runner.py:120-136) under the same deterministic policy; also the per-id episode
+    records the reference's ReplayRecorder produced (steps, max tile, score)."""
+    g = golden("runner_stack.npz")
+    m, steps, seed = [int(x) for x in g["meta"]]
+    env = oracle.OracleVecGame(m, "improved")
+    env.reset(seed)
+    counts = np.zeros(20, np.int64)
+    total = 0
+    by_id = {}
+    for t in range(steps):
+        env.prepare()
+        valid = env.observations()[1].astype(bool)
+        nvalid = valid.sum(axis=1)
+        k = (7 * t + 13 * np.arange(m)) % np.maximum(nvalid, 1)
+        rank = np.cumsum(valid, axis=1) - 1
+        acts = np.where(nvalid > 0, (valid & (rank == k[:, None])).argmax(axis=1), 0).astype(np.int64)
+        ids = env._data["id"].copy()
+        res = env.step(acts)
+        c, n = env.terminated_hist()
+        counts += c
+        total += n
+        for slot in np.flatnonzero(res["terminated"]):
+            by_id[int(ids[slot])] = (int(res["step"][slot]), int(res["state"][slot].max()), float(res["score"][slot]))
+    np.testing.assert_array_equal(counts, g["stats_counts"])
+    assert total == int(g["stats_terminated"]) and env._game_count == int(g["game_count"])
+    for i, gid in enumerate(g["buf_id"].tolist()):
+        assert by_id[gid] == (int(g["buf_steps"][i]), int(g["buf_maxcell"][i]), float(g["buf_score"][i])), gid
