@@ -40,6 +40,9 @@ ML2048_FN uint32_t ffs32(uint32_t x) { return (uint32_t)__ffs((int)x); }
 ML2048_FN uint32_t umulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 // min over three pairs of unsigned 16-bit lanes (DPX, one instruction on sm_90+)
 ML2048_FN uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+// 1 << (s mod 32): the funnel shift in wrap mode reads only the low five bits of s, so a byte of a packed word
+// can be used as a shift count without masking it first
+ML2048_FN uint32_t one_shl_wrap(uint32_t s) { return __funnelshift_l(0u, 1u, s); }
 #else
 ML2048_FN uint32_t prmt_sign(uint32_t a, uint32_t b, uint32_t s)
 {
@@ -57,6 +60,7 @@ ML2048_FN uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return prmt_sign(a
 ML2048_FN uint32_t popc32(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
 ML2048_FN uint32_t ffs32(uint32_t x) { return (uint32_t)__builtin_ffs((int)x); }
 ML2048_FN uint32_t umulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+ML2048_FN uint32_t one_shl_wrap(uint32_t s) { return 1u << (s & 31u); }
 ML2048_FN uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c)
 {
     auto mn = [](uint32_t x, uint32_t y) { return x < y ? x : y; };
@@ -80,8 +84,11 @@ constexpr uint32_t kHi = 0x80808080u;
 constexpr uint32_t kLo7 = 0x7f7f7f7fu;
 constexpr uint32_t kOnes = 0x01010101u;
 
+// bit 7 of every byte set iff the cell is non-empty (the other bits are leftovers of the add)
+ML2048_FN uint32_t occupied_signs(uint32_t row) { return add_on_fma_pipe(row, kLo7); }
+
 // 0x80 in every byte whose cell is non-empty
-ML2048_FN uint32_t occupied_flags(uint32_t row) { return add_on_fma_pipe(row, kLo7) & kHi; }
+ML2048_FN uint32_t occupied_flags(uint32_t row) { return occupied_signs(row) & kHi; }
 
 // 0xff in every byte of x that is non-zero (bytes of x must be <= 0x80)
 ML2048_FN uint32_t nonzero_mask(uint32_t x) { return prmt_sign(add_on_fma_pipe(x, kLo7), 0u, 0xba98); }
@@ -134,11 +141,10 @@ ML2048_FN void push4(uint32_t &A, uint32_t &B, uint32_t &C, uint32_t &D, Fusions
 // sum over the (up to 8) fusions of 2^(k+1): the reference's reward_fn_normal
 ML2048_FN uint32_t fusion_gain(const Fusions &f)
 {
-    // 1<<k for all eight candidate bytes; an empty candidate (k = 0) adds 1, removed afterwards
-    uint32_t s = (1u << (f.first & 0xffu)) + (1u << prmt(f.first, 0u, 0x4441)) + (1u << prmt(f.first, 0u, 0x4442)) +
-                 (1u << (f.first >> 24));
-    s += (1u << (f.second & 0xffu)) + (1u << prmt(f.second, 0u, 0x4441)) + (1u << prmt(f.second, 0u, 0x4442)) +
-         (1u << (f.second >> 24));
+    // 1<<k for all eight candidate bytes (k <= 17, so the low five bits of a byte are the whole exponent and the
+    // bits above it in the word are ignored by the wrapping shift); an empty candidate (k = 0) adds 1, removed afterwards
+    uint32_t s = one_shl_wrap(f.first) + one_shl_wrap(f.first >> 8) + one_shl_wrap(f.first >> 16) + one_shl_wrap(f.first >> 24);
+    s += one_shl_wrap(f.second) + one_shl_wrap(f.second >> 8) + one_shl_wrap(f.second >> 16) + one_shl_wrap(f.second >> 24);
     return (s - 8u + f.count) << 1;
 }
 
@@ -170,38 +176,56 @@ ML2048_FN void fusion_log(const Fusions &f, uint32_t &m0, uint32_t &m1, uint32_t
     m3 = (m3 | (m3 << 8)) & 0x00ff00ffu; m3 = (m3 | (m3 << 4)) & 0x0f0f0f0fu;
 }
 
-ML2048_FN void transpose4x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3)
+// The move itself: direction dispatch of _step_kernel (game_numba.py:93-134) without a branch AND without selects.
+// The lines a move pushes reach push4 through a two-stage byte-permute network (PRMT takes its selector from a
+// register), and the pushed words go back to rows through a second one; what differs between the four directions is
+// only the six selectors: for UP/DOWN the network passes the rows through (in reverse order for DOWN), for LEFT/RIGHT it
+// is the 4x4 byte transpose (with the columns taken in reverse order for RIGHT).  One 32-byte row of this table per
+// action: {in1a, in1b, in2a, in2b, out2a, out2b, 0, 0}; the step kernel keeps the table in shared memory and fetches a
+// game's row with two vector loads instead of deciding per word with compare + select (16 SEL per move before).
+//   stage 1: t0 = P(r0,r2,in1a) t1 = P(r1,r3,in1a) t2 = P(r0,r2,in1b) t3 = P(r1,r3,in1b)
+//   stage 2: A = P(t0,t1,in2a) B = P(t0,t1,in2b) C = P(t2,t3,in2a) D = P(t2,t3,in2b)
+//   back   : u0 = P(A,C,in2a) u1 = P(B,D,in2a) u2 = P(A,C,in2b) u3 = P(B,D,in2b)
+//            r0 = P(u0,u1,out2a) r1 = P(u0,u1,out2b) r2 = P(u2,u3,out2a) r3 = P(u2,u3,out2b)
+constexpr int kMoveSelRow = 8;  // words per action
+#define ML2048_MOVE_SEL_TABLE                                                     \
+    {                                                                             \
+        0x5140u, 0x7362u, 0x5140u, 0x7362u, 0x5140u, 0x7362u, 0u, 0u, /* left  */ \
+        0x6273u, 0x4051u, 0x5140u, 0x7362u, 0x0415u, 0x2637u, 0u, 0u, /* right */ \
+        0x3210u, 0x7654u, 0x3210u, 0x7654u, 0x3210u, 0x7654u, 0u, 0u, /* up    */ \
+        0x7654u, 0x3210u, 0x7654u, 0x3210u, 0x7654u, 0x3210u, 0u, 0u  /* down  */ \
+    }
+
+// `sel` = the action's row of the table (16-byte aligned)
+ML2048_FN void move_board_sel(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, const uint32_t *sel, Fusions &f)
 {
-    const uint32_t t0 = prmt(r0, r1, 0x5140);  // r0.0 r1.0 r0.1 r1.1
-    const uint32_t t1 = prmt(r2, r3, 0x5140);
-    const uint32_t t2 = prmt(r0, r1, 0x7362);  // r0.2 r1.2 r0.3 r1.3
-    const uint32_t t3 = prmt(r2, r3, 0x7362);
-    r0 = prmt(t0, t1, 0x5410);
-    r1 = prmt(t0, t1, 0x7632);
-    r2 = prmt(t2, t3, 0x5410);
-    r3 = prmt(t2, t3, 0x7632);
+#if defined(__CUDACC__)
+    const uint4 sa = *reinterpret_cast<const uint4 *>(sel);
+    const uint2 sb = *reinterpret_cast<const uint2 *>(sel + 4);
+    const uint32_t in1a = sa.x, in1b = sa.y, in2a = sa.z, in2b = sa.w, out2a = sb.x, out2b = sb.y;
+#else
+    const uint32_t in1a = sel[0], in1b = sel[1], in2a = sel[2], in2b = sel[3], out2a = sel[4], out2b = sel[5];
+#endif
+    // prmt_sign = the raw PRMT (no selector nibble of the table has its sign-replication bit set); __byte_perm would
+    // first mask a selector it cannot see to 0x7777
+    const uint32_t t0 = prmt_sign(r0, r2, in1a), t1 = prmt_sign(r1, r3, in1a), t2 = prmt_sign(r0, r2, in1b), t3 = prmt_sign(r1, r3, in1b);
+    uint32_t A = prmt_sign(t0, t1, in2a), B = prmt_sign(t0, t1, in2b), C = prmt_sign(t2, t3, in2a), D = prmt_sign(t2, t3, in2b);
+    push4(A, B, C, D, f);
+    const uint32_t u0 = prmt_sign(A, C, in2a), u1 = prmt_sign(B, D, in2a), u2 = prmt_sign(A, C, in2b), u3 = prmt_sign(B, D, in2b);
+    r0 = prmt_sign(u0, u1, out2a);
+    r1 = prmt_sign(u0, u1, out2b);
+    r2 = prmt_sign(u2, u3, out2a);
+    r3 = prmt_sign(u2, u3, out2b);
 }
 
-// The move itself: direction dispatch of _step_kernel (game_numba.py:93-134) without a branch.
-// action bit 1 = vertical (lines are columns: the rows already are the lane-parallel words),
-// bit 0 = toward the high end (the wall is at the other end: A..D are taken in reverse order).
+#if !defined(__CUDACC__)
+// host build (tests/host_shim): the table is a plain static array
 ML2048_FN void move_board(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t action, Fusions &f)
 {
-    const bool vertical = (action & 2u) != 0u;
-    const bool reverse = (action & 1u) != 0u;
-    uint32_t c0 = r0, c1 = r1, c2 = r2, c3 = r3;
-    transpose4x4(c0, c1, c2, c3);
-    const uint32_t x0 = vertical ? r0 : c0, x1 = vertical ? r1 : c1, x2 = vertical ? r2 : c2, x3 = vertical ? r3 : c3;
-    uint32_t A = reverse ? x3 : x0, B = reverse ? x2 : x1, C = reverse ? x1 : x2, D = reverse ? x0 : x3;
-    push4(A, B, C, D, f);
-    const uint32_t y0 = reverse ? D : A, y1 = reverse ? C : B, y2 = reverse ? B : C, y3 = reverse ? A : D;
-    c0 = y0, c1 = y1, c2 = y2, c3 = y3;
-    transpose4x4(c0, c1, c2, c3);
-    r0 = vertical ? y0 : c0;
-    r1 = vertical ? y1 : c1;
-    r2 = vertical ? y2 : c2;
-    r3 = vertical ? y3 : c3;
+    static const uint32_t table[4 * kMoveSelRow] = ML2048_MOVE_SEL_TABLE;
+    move_board_sel(r0, r1, r2, r3, table + (action & 3u) * kMoveSelRow, f);
 }
+#endif
 
 // Valid-action mask, one byte per direction (left,right,up,down), as the little-endian word the
 // reference stores in `valid_actions` (game_numba.py:259-289).  A direction is valid iff some tile
@@ -232,15 +256,17 @@ ML2048_FN uint32_t valid_mask(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3
     return (l + r * 0x100u) + (u * 0x10000u + d * 0x1000000u);  // disjoint bytes: adds (IMAD) instead of shifts + ORs
 }
 
-// Write `value` into cell `cell` (0..15) of the board.
+// Write `value` into cell `cell` (0..15) of the (empty there) board: one 64-bit shift places it inside its half of
+// the board, one predicate picks the half.
 ML2048_FN void put_cell(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t cell, uint32_t value)
 {
-    const uint32_t v = value << ((cell & 3u) * 8u);
-    const uint32_t row = cell >> 2;
-    r0 |= (row == 0u) ? v : 0u;
-    r1 |= (row == 1u) ? v : 0u;
-    r2 |= (row == 2u) ? v : 0u;
-    r3 |= (row == 3u) ? v : 0u;
+    const unsigned long long v = (unsigned long long)value << ((cell & 7u) * 8u);
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const bool top = (cell & 8u) != 0u;
+    r0 |= top ? 0u : lo;
+    r1 |= top ? 0u : hi;
+    r2 |= top ? lo : 0u;
+    r3 |= top ? hi : 0u;
 }
 
 // Replay-mode spawn position.  The reference walks row `p` of randperm and takes the first entry whose
@@ -248,19 +274,28 @@ ML2048_FN void put_cell(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, 
 // the smallest RANK in that row.  `keys` is the row in inverse form, keys[c] = 16*rank(c) + c (see
 // ml2048_pack_randperm_keys); one min-reduction over the sixteen keys (as 16-bit lanes, DPX three-input
 // min), with occupied cells pushed out of range, yields the winner.  Returns the cell, or 16 if the board is full.
+// n0..n3: bit 7 of every byte set iff the cell is occupied; the other bits are ignored (so `row + 0x7f7f7f7f` will do).
+ML2048_FN uint32_t first_empty_key(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t n0, uint32_t n1, uint32_t n2,
+                                   uint32_t n3)
+{
+    // widen every key byte to a 16-bit lane whose HIGH byte is 0xff when the cell is occupied (one PRMT takes the key
+    // byte and replicates the sign of the occupancy byte next to it), so any occupied lane (>= 0xff00) loses against
+    // any empty one (<= 0x00ff)
+    const uint32_t a0 = prmt_sign(k0, n0, 0xd1c0), a1 = prmt_sign(k0, n0, 0xf3e2);
+    const uint32_t b0 = prmt_sign(k1, n1, 0xd1c0), b1 = prmt_sign(k1, n1, 0xf3e2);
+    const uint32_t c0 = prmt_sign(k2, n2, 0xd1c0), c1 = prmt_sign(k2, n2, 0xf3e2);
+    const uint32_t d0 = prmt_sign(k3, n3, 0xd1c0), d1 = prmt_sign(k3, n3, 0xf3e2);
+    const uint32_t m = min3_u16x2(min3_u16x2(a0, a1, b0), min3_u16x2(b1, c0, c1), min3_u16x2(d0, d1, d1));
+    // both halves of the result = the smaller half: its low byte is the winning key (low nibble = the cell), its high
+    // byte is 0xff iff the board is full
+    return min3_u16x2(m, prmt(m, 0u, 0x1032), m);
+}
+
+// The cell (0..15), or 16 if the board is full.
 ML2048_FN uint32_t first_empty_by_rank(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t n0, uint32_t n1,
                                        uint32_t n2, uint32_t n3)
 {
-    // widen every key byte to a 16-bit lane whose HIGH byte is 0xff when the cell is occupied, so any
-    // occupied lane (>= 0xff00) loses against any empty one (<= 0x00ff)
-    const uint32_t o0 = prmt_sign(n0, 0u, 0xba98), o1 = prmt_sign(n1, 0u, 0xba98);
-    const uint32_t o2 = prmt_sign(n2, 0u, 0xba98), o3 = prmt_sign(n3, 0u, 0xba98);
-    const uint32_t a0 = prmt(k0, o0, 0x5140), a1 = prmt(k0, o0, 0x7362);
-    const uint32_t b0 = prmt(k1, o1, 0x5140), b1 = prmt(k1, o1, 0x7362);
-    const uint32_t c0 = prmt(k2, o2, 0x5140), c1 = prmt(k2, o2, 0x7362);
-    const uint32_t d0 = prmt(k3, o3, 0x5140), d1 = prmt(k3, o3, 0x7362);
-    uint32_t m = min3_u16x2(min3_u16x2(a0, a1, b0), min3_u16x2(b1, c0, c1), min3_u16x2(d0, d1, d1));
-    m = (m & 0xffffu) < (m >> 16) ? (m & 0xffffu) : (m >> 16);
+    const uint32_t m = first_empty_key(k0, k1, k2, k3, n0, n1, n2, n3) & 0xffffu;
     return m >= 0xff00u ? 16u : (m & 15u);
 }
 

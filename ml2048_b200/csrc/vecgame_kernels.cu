@@ -191,6 +191,9 @@ __device__ __forceinline__ void write_onehot_warp_dyn(int dtype, uint4 board, vo
 
 // ---- the step kernel ------------------------------------------------------------------------
 
+// direction -> permute selectors of the move (board_ops.cuh); copied to shared memory by every block
+__constant__ uint32_t c_move_sel[4 * kMoveSelRow] = ML2048_MOVE_SEL_TABLE;
+
 __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, int64_t g)
 {
     if (dtype == ML2048_ACT_U8) return reinterpret_cast<const uint8_t *>(actions)[g];
@@ -208,6 +211,9 @@ template <int kRng, bool kLog, int kOneHot, bool kFull, int kThreads>
 __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a)
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kThreads : 1];
+    __shared__ __align__(16) uint32_t s_move_sel[4 * kMoveSelRow];
+    if (threadIdx.x < 4 * kMoveSelRow) s_move_sel[threadIdx.x] = c_move_sel[threadIdx.x];
+    __syncthreads();
 #if defined(ML2048_ONEHOT_TMA)
     extern __shared__ __align__(128) uint4 tma_stage[];  // [kTmaStages][kTmaChunkBytes] when launched with dynamic shared memory
 #endif
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
         float tr_reward = 0.0f, tr_score = 0.0f;
         int32_t tr_step = 0;
         uint32_t tr_term = 0u, tr_mask = 0u;
-        move_board(r0, r1, r2, r3, action & 3u, f);
+        move_board_sel(r0, r1, r2, r3, s_move_sel + (action & 3u) * kMoveSelRow, f);
         // valid_actions[action] (game_numba.py:718) == "the move changes the board"; out-of-range
         // actions (which the reference would index out of bounds with) count as invalid moves
         const bool moved = (action < 4u) && (((r0 ^ bd.x) | (r1 ^ bd.y) | (r2 ^ bd.z) | (r3 ^ bd.w)) != 0u);
@@ -289,20 +295,22 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
             const int32_t nstep = a.step[g] + 1;
 
             // spawn one tile (_spawn2 with count = 1, game_numba.py:733)
-            const uint32_t n0 = occupied_flags(r0), n1 = occupied_flags(r1), n2 = occupied_flags(r2), n3 = occupied_flags(r3);
+            const uint32_t n0 = occupied_signs(r0), n1 = occupied_signs(r1), n2 = occupied_signs(r2), n3 = occupied_signs(r3);
             uint32_t cell, value;
             if (kRng == ML2048_RNG_REPLAY) {
                 const uint32_t row = (uint32_t)((uint64_t)(rand_seed + (int64_t)slot) % (uint64_t)kRandRows);
                 const uint4 keys = __ldg(reinterpret_cast<const uint4 *>(keys_table) + row);
-                cell = first_empty_by_rank(keys.x, keys.y, keys.z, keys.w, n0, n1, n2, n3);
-                value = 2u - ((two_mask >> (cell & 15u)) & 1u);
+                // a move that changed the board leaves at least one empty cell (a slide vacates one, a fusion frees
+                // one), so the search cannot come back empty-handed here
+                cell = first_empty_key(keys.x, keys.y, keys.z, keys.w, n0, n1, n2, n3) & 15u;
+                value = 2u - ((two_mask >> cell) & 1u);
             } else {
-                const uint32_t empties = empties16(n0 ^ kHi, n1 ^ kHi, n2 ^ kHi, n3 ^ kHi);
-                const uint32_t ne = popc32(empties);
-                cell = ne ? kth_set_bit16(empties, umulhi32(rnd.x, ne)) : 16u;
+                const uint32_t empties = empties16(~n0 & kHi, ~n1 & kHi, ~n2 & kHi, ~n3 & kHi);
+                const uint32_t ne = popc32(empties);  // >= 1, see above
+                cell = kth_set_bit16(empties, umulhi32(rnd.x, ne));
                 value = (rnd.y < a.two_threshold) ? 1u : 2u;
             }
-            if (cell < 16u) put_cell(r0, r1, r2, r3, cell, value);
+            put_cell(r0, r1, r2, r3, cell, value);
 
             const uint32_t vm = valid_mask(r0, r1, r2, r3);
             const bool dead = vm == 0u;
