@@ -181,7 +181,7 @@ ML2048_FN void fusion_log(const Fusions &f, uint32_t &m0, uint32_t &m1, uint32_t
 // register), and the pushed words go back to rows through a second one; what differs between the four directions is
 // only the six selectors: for UP/DOWN the network passes the rows through (in reverse order for DOWN), for LEFT/RIGHT it
 // is the 4x4 byte transpose (with the columns taken in reverse order for RIGHT).  One 32-byte row of this table per
-// action: {in1a, in1b, in2a, in2b, out2a, out2b, 0, 0}; the step kernel keeps the table in shared memory and fetches a
+// action: {in1a, in1b, in2a, in2b, out2a, out2b, 0, 0}; the step kernel keeps the table in global memory (L1) and fetches a
 // game's row with two vector loads instead of deciding per word with compare + select (16 SEL per move before).
 //   stage 1: t0 = P(r0,r2,in1a) t1 = P(r1,r3,in1a) t2 = P(r0,r2,in1b) t3 = P(r1,r3,in1b)
 //   stage 2: A = P(t0,t1,in2a) B = P(t0,t1,in2b) C = P(t2,t3,in2a) D = P(t2,t3,in2b)
@@ -200,8 +200,8 @@ constexpr int kMoveSelRow = 8;  // words per action
 ML2048_FN void move_board_sel(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, const uint32_t *sel, Fusions &f)
 {
 #if defined(__CUDACC__)
-    const uint4 sa = *reinterpret_cast<const uint4 *>(sel);
-    const uint2 sb = *reinterpret_cast<const uint2 *>(sel + 4);
+    const uint4 sa = __ldg(reinterpret_cast<const uint4 *>(sel));
+    const uint2 sb = __ldg(reinterpret_cast<const uint2 *>(sel + 4));
     const uint32_t in1a = sa.x, in1b = sa.y, in2a = sa.z, in2b = sa.w, out2a = sb.x, out2b = sb.y;
 #else
     const uint32_t in1a = sel[0], in1b = sel[1], in2a = sel[2], in2b = sel[3], out2a = sel[4], out2b = sel[5];

@@ -191,8 +191,9 @@ __device__ __forceinline__ void write_onehot_warp_dyn(int dtype, uint4 board, vo
 
 // ---- the step kernel ------------------------------------------------------------------------
 
-// direction -> permute selectors of the move (board_ops.cuh); copied to shared memory by every block
-__constant__ uint32_t c_move_sel[4 * kMoveSelRow] = ML2048_MOVE_SEL_TABLE;
+// direction -> permute selectors of the move (board_ops.cuh): 128 bytes that live in L1; a game's row is fetched with two
+// read-only vector loads (no shared-memory copy, so no barrier at the start of the block)
+__device__ const uint32_t d_move_sel[4 * kMoveSelRow] = ML2048_MOVE_SEL_TABLE;
 
 __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, int64_t g)
 {
@@ -208,12 +209,10 @@ __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, 
 // kFull adds the rollout extras (policy-logits sampling, transition record, episode log); the lean variant
 // compiles them out so the plain step pays nothing for them.
 template <int kRng, bool kLog, int kOneHot, bool kFull, int kThreads>
-__global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a)
+// 256-thread blocks: 8 per SM (all 2048 thread slots) needs <= 32 registers
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 8 : 2) step_kernel(const ml2048_step_args a)
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kThreads : 1];
-    __shared__ __align__(16) uint32_t s_move_sel[4 * kMoveSelRow];
-    if (threadIdx.x < 4 * kMoveSelRow) s_move_sel[threadIdx.x] = c_move_sel[threadIdx.x];
-    __syncthreads();
 #if defined(ML2048_ONEHOT_TMA)
     extern __shared__ __align__(128) uint4 tma_stage[];  // [kTmaStages][kTmaChunkBytes] when launched with dynamic shared memory
 #endif
@@ -267,7 +266,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
         float tr_reward = 0.0f, tr_score = 0.0f;
         int32_t tr_step = 0;
         uint32_t tr_term = 0u, tr_mask = 0u;
-        move_board_sel(r0, r1, r2, r3, s_move_sel + (action & 3u) * kMoveSelRow, f);
+        move_board_sel(r0, r1, r2, r3, d_move_sel + (action & 3u) * kMoveSelRow, f);
         // valid_actions[action] (game_numba.py:718) == "the move changes the board"; out-of-range
         // actions (which the reference would index out of bounds with) count as invalid moves
         const bool moved = (action < 4u) && (((r0 ^ bd.x) | (r1 ^ bd.y) | (r2 ^ bd.z) | (r3 ^ bd.w)) != 0u);
@@ -291,7 +290,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const ml2048_step_args a
             } else {
                 reward = (float)gain;
             }
-            const float score = a.score[g] + (float)gain;
+                        const float score = a.score[g] + (float)gain;
             const int32_t nstep = a.step[g] + 1;
 
             // spawn one tile (_spawn2 with count = 1, game_numba.py:733)
