@@ -458,8 +458,9 @@ def run_b200_arm(args: argparse.Namespace) -> None:
             },
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": 4 * k_steps,
-            "launches_per_step": "prepare_count, prepare_scan, prepare_apply, step_kernel",
+            "gpu_launches": (4 if os.environ.get("ML2048_PREPARE", "").startswith("s") else 2) * k_steps,
+            "launches_per_step": ("prepare_count, prepare_scan, prepare_apply, step_kernel" if os.environ.get("ML2048_PREPARE", "").startswith("s")
+                                  else "prepare_fused_kernel (one cooperative launch), step_kernel"),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "episode_stats": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in stats_d.items()},

@@ -237,7 +237,10 @@ ML2048_API int64_t ml2048_prepare_scratch_ints(int64_t num_games);
 /* _vec_step + VecGame.step body: game_numba.py:660-738 */
 ML2048_API int ml2048_step(const ml2048_step_args *args, void *stream);
 
-/* VecGame.prepare reset loop: game_numba.py:629-658.  ml2048_prepare = count + apply.  The two halves
+/* VecGame.prepare reset loop: game_numba.py:629-658.  ml2048_prepare runs it in one launch: a single-block kernel up to
+ * 8192 games, above that one cooperative launch (a grid of co-resident blocks with one grid-wide barrier between counting
+ * and resetting; needs cudaDevAttrCooperativeLaunch, else -- or with ML2048_PREPARE=split in the environment, or for
+ * shards too large for it -- count + apply below).  Semantically ml2048_prepare = count + apply.  The two halves
  * are exported so a multi-GPU caller can exchange per-rank reset counts between them (all_gather of
  * *reset_count -> id_offset) and keep ids globally slot-ordered like the single-process reference:
  *   count: np.flatnonzero(terminated) bookkeeping (:629) -> *reset_count, slot-ordered offsets in scratch

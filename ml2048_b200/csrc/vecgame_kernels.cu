@@ -8,14 +8,17 @@
 // fully coalesced 32 B..512 B access.  The fused one-hot observation (1 KiB per game in fp32) is
 // written cooperatively by the whole block from boards staged in shared memory so that each warp
 // store instruction covers 512 contiguous bytes.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/ml2048_b200.h"
 #include "board_ops.cuh"
 
 using namespace ml2048;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -479,6 +482,85 @@ __global__ void __launch_bounds__(1024) prepare_scan_kernel(int32_t *tile_counts
     }
 }
 
+// The random inputs of one prepare(): scalar arguments, or the pre-drawn schedule entry a CUDA graph replays.
+struct PrepDraws {
+    int64_t rand_base;
+    uint32_t two_mask;
+    uint64_t philox_counter;
+    const uint8_t *perm_table;
+};
+
+__device__ __forceinline__ PrepDraws load_prep_draws(const ml2048_prepare_args &a)
+{
+    PrepDraws d{a.rand_base, a.two_mask, a.philox_counter, a.randperm};
+    if (a.sched) {
+        const ml2048_sched_entry e = a.sched[*a.sched_cursor];
+        d.rand_base = e.rand_base;
+        d.two_mask = e.two_mask;
+        d.philox_counter = e.philox_counter;
+        d.perm_table += (int64_t)e.table * a.table_stride;
+    }
+    return d;
+}
+
+// The reset body of VecGame.prepare for ONE slot (game_numba.py:634-656): zero the record, id = id_base + order (the
+// rank of the slot among all slots reset by this call: slot-ordered like :641-644), two spawned tiles, the mask.
+// Returns the fresh board.
+template <int kRng>
+__device__ __forceinline__ uint4 reset_slot(const ml2048_prepare_args &a, const PrepDraws &d, int64_t g, int64_t order, int64_t id_base)
+{
+    const uint64_t slot = (uint64_t)(a.slot_base + g);
+    uint32_t c0, c1, v0, v1;
+    if (kRng == ML2048_RNG_REPLAY) {
+        // the board is empty, so the first two entries of the table row are taken (game_numba.py:648-655)
+        const uint32_t row = (uint32_t)((uint64_t)(d.rand_base + (int64_t)slot) % (uint64_t)kRandRows);
+        const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(d.perm_table) + row * 4);
+        c0 = p & 0xffu;
+        c1 = (p >> 8) & 0xffu;
+        v0 = 2u - ((d.two_mask >> (c0 & 15u)) & 1u);
+        v1 = 2u - ((d.two_mask >> (c1 & 15u)) & 1u);
+    } else {
+        const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)d.philox_counter,
+                                        (uint32_t)(d.philox_counter >> 32) ^ 0x80000000u, (uint32_t)a.philox_seed,
+                                        (uint32_t)(a.philox_seed >> 32));
+        c0 = rnd.x >> 28;
+        c1 = umulhi32(rnd.y, 15u);
+        c1 += (c1 >= c0) ? 1u : 0u;
+        v0 = (rnd.z < a.two_threshold) ? 1u : 2u;
+        v1 = (rnd.w < a.two_threshold) ? 1u : 2u;
+    }
+    uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u;
+    put_cell(r0, r1, r2, r3, c0 & 15u, v0);
+    put_cell(r0, r1, r2, r3, c1 & 15u, v1);
+    const uint4 bd = make_uint4(r0, r1, r2, r3);
+    reinterpret_cast<uint4 *>(a.board)[g] = bd;
+    reinterpret_cast<uint32_t *>(a.valid)[g] = valid_mask(r0, r1, r2, r3);
+    a.id[g] = (int32_t)(id_base + order);
+    a.step[g] = 0;
+    a.score[g] = 0.0f;
+    a.reward[g] = 0.0f;
+    a.invalid[g] = 0;
+    if (a.merged) reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(0, 0, 0, 0);
+    if (a.age) a.age[g] = 0;
+    if (a.reset_indices) a.reset_indices[order] = g;
+    return bd;
+}
+
+// The one-hot rows of the games the lanes of a warp just reset (`has`), written by the whole warp one game after the
+// other so that every store instruction covers 512 contiguous bytes.
+__device__ __forceinline__ void write_onehot_of_lanes(const ml2048_prepare_args &a, bool has, uint4 bd, long long g, int lane)
+{
+    uint32_t ballot = __ballot_sync(0xffffffffu, has);
+    while (ballot) {
+        const int src = __ffs((int)ballot) - 1;
+        ballot &= ballot - 1u;
+        const uint4 b = make_uint4(__shfl_sync(0xffffffffu, bd.x, src), __shfl_sync(0xffffffffu, bd.y, src),
+                                   __shfl_sync(0xffffffffu, bd.z, src), __shfl_sync(0xffffffffu, bd.w, src));
+        const long long gg = __shfl_sync(0xffffffffu, g, src);
+        write_onehot_warp_dyn(a.onehot_dtype, b, a.onehot, gg, lane);
+    }
+}
+
 // Reset pass over one tile of 4096 slots by one block.  `tile_offset` = finished games in earlier tiles, `id_base` = id of
 // the first game reset by this prepare().  Returns the number of games this tile reset (to every thread).
 template <int kRng>
@@ -503,18 +585,7 @@ __device__ __forceinline__ int apply_tile(const ml2048_prepare_args &a, int64_t 
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += warp_tot[w];
     const bool had_any = mask != 0u;
     const int lane = threadIdx.x & 31;
-
-    int64_t rand_base = a.rand_base;
-    uint32_t two_mask = a.two_mask;
-    uint64_t philox_counter = a.philox_counter;
-    const uint8_t *perm_table = a.randperm;
-    if (a.sched) {
-        const ml2048_sched_entry e = a.sched[*a.sched_cursor];
-        rand_base = e.rand_base;
-        two_mask = e.two_mask;
-        philox_counter = e.philox_counter;
-        perm_table += (int64_t)e.table * a.table_stride;
-    }
+    const PrepDraws draws = load_prep_draws(a);
     int tile_total = 0;
 #pragma unroll
     for (int w = 0; w < kPrepThreads / 32; ++w) tile_total += warp_tot[w];
@@ -527,56 +598,13 @@ __device__ __forceinline__ int apply_tile(const ml2048_prepare_args &a, int64_t 
         uint4 bd = make_uint4(0u, 0u, 0u, 0u);
         long long g = 0;
         if (has) {
-        const int j = __ffs((int)mask) - 1;
-        mask &= mask - 1u;
-        g = i * 16 + j;
-        const uint64_t slot = (uint64_t)(a.slot_base + g);
-        uint32_t c0, c1, v0, v1;
-        if (kRng == ML2048_RNG_REPLAY) {
-            // the board is empty, so the first two entries of the table row are taken (game_numba.py:648-655)
-            const uint32_t row = (uint32_t)((uint64_t)(rand_base + (int64_t)slot) % (uint64_t)kRandRows);
-            const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(perm_table) + row * 4);
-            c0 = p & 0xffu;
-            c1 = (p >> 8) & 0xffu;
-            v0 = 2u - ((two_mask >> (c0 & 15u)) & 1u);
-            v1 = 2u - ((two_mask >> (c1 & 15u)) & 1u);
-        } else {
-            const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)philox_counter,
-                                            (uint32_t)(philox_counter >> 32) ^ 0x80000000u, (uint32_t)a.philox_seed,
-                                            (uint32_t)(a.philox_seed >> 32));
-            c0 = rnd.x >> 28;
-            c1 = umulhi32(rnd.y, 15u);
-            c1 += (c1 >= c0) ? 1u : 0u;
-            v0 = (rnd.z < a.two_threshold) ? 1u : 2u;
-            v1 = (rnd.w < a.two_threshold) ? 1u : 2u;
+            const int j = __ffs((int)mask) - 1;
+            mask &= mask - 1u;
+            g = i * 16 + j;
+            bd = reset_slot<kRng>(a, draws, g, order, id_base);
+            order += 1;
         }
-        uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u;
-        put_cell(r0, r1, r2, r3, c0 & 15u, v0);
-        put_cell(r0, r1, r2, r3, c1 & 15u, v1);
-        bd = make_uint4(r0, r1, r2, r3);
-        reinterpret_cast<uint4 *>(a.board)[g] = bd;
-        reinterpret_cast<uint32_t *>(a.valid)[g] = valid_mask(r0, r1, r2, r3);
-        a.id[g] = (int32_t)(id_base + order);
-        a.step[g] = 0;
-        a.score[g] = 0.0f;
-        a.reward[g] = 0.0f;
-        a.invalid[g] = 0;
-        if (a.merged) reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(0, 0, 0, 0);
-        if (a.age) a.age[g] = 0;
-        if (a.reset_indices) a.reset_indices[order] = g;
-        order += 1;
-        }
-        if (a.onehot) {
-            uint32_t ballot = __ballot_sync(0xffffffffu, has);
-            while (ballot) {
-                const int src = __ffs((int)ballot) - 1;
-                ballot &= ballot - 1u;
-                const uint4 b = make_uint4(__shfl_sync(0xffffffffu, bd.x, src), __shfl_sync(0xffffffffu, bd.y, src),
-                                           __shfl_sync(0xffffffffu, bd.z, src), __shfl_sync(0xffffffffu, bd.w, src));
-                const long long gg = __shfl_sync(0xffffffffu, g, src);
-                write_onehot_warp_dyn(a.onehot_dtype, b, a.onehot, gg, lane);
-            }
-        }
+        if (a.onehot) write_onehot_of_lanes(a, has, bd, g, lane);
     }
     // every flag this thread saw is now cleared (entry.fill(0), game_numba.py:638-639)
     if (had_any) reinterpret_cast<uint4 *>(a.terminated)[i] = make_uint4(0, 0, 0, 0);
@@ -610,6 +638,134 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_small_kernel(const ml204
     if (threadIdx.x == 0) {
         *a.game_count = id_base + running;
         *a.reset_count = running;
+    }
+}
+
+// Large batches: the whole auto-reset in ONE cooperative launch.  A grid that fits the GPU in a single wave splits the
+// slots into contiguous ranges, one per block, and every thread owns a run of consecutive 16-slot groups of it.
+// Phase 1: the thread reads the `terminated` flags of its groups ONCE (all loads in flight together), keeps them as bit
+// masks in shared memory, clears them in HBM; the block publishes how many of its games are over.  One grid-wide
+// barrier.  Phase 2: every block sums the counts of the blocks before it (= the slot-ordered rank of its first finished
+// game), lists its finished games in slot order in shared memory (one block scan) and resets them with CONVERGENT lanes
+// (thread j takes list entry j) instead of one or two live lanes per warp walking a 512-slot stretch; the one-hot rows
+// of the reset games are then written by all threads of the block from the boards parked in shared memory.
+// Measured at M = 2^24, steady state (0.93 % of the games over), tools/prepare_probe.py with a cold L2: 65 us against
+// 68.7 us for count + scan + apply; in the rollout loop 55 against 60 us (93 against 96 us with the fp32 one-hot rows).
+// Launch + phase 1 + barrier are 15 us of that; the rest is the scattered stores of the 156 000 reset games themselves
+// (eight arrays, one partly written 32-byte sector each), which the three-launch path pays as well.
+constexpr int kFusedGroupsPerThread = 32;                             // at most
+constexpr int kFusedMaxGroups = kPrepThreads * kFusedGroupsPerThread;  // 16-slot groups per block (masks: 16 KiB)
+constexpr int kFusedListCap = 1024;                                    // finished games reset per pass
+
+// all threads of the block write the one-hot rows of `n` games whose boards and slots are in shared memory
+template <int kDtype>
+__device__ __forceinline__ void write_onehot_listed(const uint4 *boards, const uint32_t *slots, int n, void *out_base)
+{
+    using P = OneHotPiece<kDtype>;
+    constexpr int kPer = P::kPiecesPerGame;
+    constexpr int kGamesPerPass = kPrepThreads / kPer;
+    typename P::vec *out = reinterpret_cast<typename P::vec *>(out_base);
+    const int piece = threadIdx.x % kPer;
+    for (int j = threadIdx.x / kPer; j < n; j += kGamesPerPass)
+        store_streaming(out + (int64_t)slots[j] * kPer + piece, P::make(boards, j, piece));
+}
+
+template <int kRng>
+__global__ void __launch_bounds__(kPrepThreads, 5) prepare_fused_kernel(const ml2048_prepare_args a, int32_t *block_counts)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint16_t s_mask[kFusedMaxGroups];
+    __shared__ uint32_t s_list[kFusedListCap];
+    __shared__ uint4 s_board[kFusedListCap];
+    __shared__ int warp_tot[kPrepThreads / 32];
+    const int64_t n16 = (a.num_games + 15) / 16;
+    const int64_t per_block = (n16 + gridDim.x - 1) / gridDim.x;
+    const int64_t begin = (int64_t)blockIdx.x * per_block;
+    const int64_t end = begin + per_block < n16 ? begin + per_block : n16;
+    const int groups = end > begin ? (int)(end - begin) : 0;
+    const int per_thread = (int)((per_block + kPrepThreads - 1) / kPrepThreads);  // <= kFusedGroupsPerThread
+    const int k_first = threadIdx.x * per_thread;
+    const int k_last = k_first + per_thread < groups ? k_first + per_thread : groups;  // this thread owns [k_first, k_last)
+    const int64_t id_base = *a.game_count;  // read before the barrier; block 0 advances it after the barrier
+
+    // phase 1: flags -> masks in shared memory, flags cleared (entry.fill(0), game_numba.py:638-639), block count.
+    // A thread's groups are adjacent (16 bytes each), so a warp's loads cover one dense stretch; four at a time
+    int mine = 0;
+    for (int k0 = k_first; k0 < k_last; k0 += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            v[u] = k0 + u < k_last ? reinterpret_cast<const uint4 *>(a.terminated)[begin + k0 + u] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (k0 + u < k_last) {
+                const uint32_t m = flags16(v[u]);
+                s_mask[k0 + u] = (uint16_t)m;
+                mine += __popc(m);
+                if (m) reinterpret_cast<uint4 *>(a.terminated)[begin + k0 + u] = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+    const int block_total = block_sum_256(mine, warp_tot);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = block_total;
+    grid.sync();
+
+    // finished games in the blocks before this one, and in all blocks
+    int before = 0, all = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kPrepThreads) {
+        const int c = block_counts[b];
+        all += c;
+        before += b < (int)blockIdx.x ? c : 0;
+    }
+    __syncthreads();
+    before = block_sum_256(before, warp_tot);
+    __syncthreads();
+    all = block_sum_256(all, warp_tot);
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *a.game_count = id_base + all;
+        *a.reset_count = all;
+    }
+    if (block_total == 0) return;
+
+    // phase 2: rank of this thread's first finished game inside the block (exclusive scan of `mine`)
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += n;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int my_first = inc - mine;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) my_first += warp_tot[w];
+
+    const PrepDraws draws = load_prep_draws(a);
+    // passes of kFusedListCap games (one pass unless a large share of the block's games is over, e.g. right after reset())
+    for (int window = 0; window < block_total; window += kFusedListCap) {
+        const int n = block_total - window < kFusedListCap ? block_total - window : kFusedListCap;
+        if (my_first < window + n && my_first + mine > window) {  // some of this thread's games fall into the window
+            int p = my_first - window;
+            for (int k = k_first; k < k_last; ++k) {
+                uint32_t m = s_mask[k];
+                const uint32_t g0 = (uint32_t)((begin + k) * 16);
+                while (m) {
+                    if (p >= 0 && p < n) s_list[p] = g0 + (uint32_t)(__ffs((int)m) - 1);
+                    ++p;
+                    m &= m - 1u;
+                }
+            }
+        }
+        __syncthreads();  // the list is complete
+        for (int j = threadIdx.x; j < n; j += kPrepThreads)
+            s_board[j] = reset_slot<kRng>(a, draws, s_list[j], (int64_t)before + window + j, id_base);
+        if (a.onehot) {
+            __syncthreads();  // the boards are parked
+            if (a.onehot_dtype == ML2048_ONEHOT_F32) write_onehot_listed<ML2048_ONEHOT_F32>(s_board, s_list, n, a.onehot);
+            else if (a.onehot_dtype == ML2048_ONEHOT_BF16) write_onehot_listed<ML2048_ONEHOT_BF16>(s_board, s_list, n, a.onehot);
+            else write_onehot_listed<ML2048_ONEHOT_U8>(s_board, s_list, n, a.onehot);
+        }
+        __syncthreads();  // list and boards may be overwritten
     }
 }
 
@@ -907,6 +1063,33 @@ int ml2048_prepare_apply(const ml2048_prepare_args *args, void *stream)
     return launch_status();
 }
 
+// Single-wave cooperative launch of the fused auto-reset; ML2048_E_SIZE when the batch is too large for it.
+static int launch_prepare_fused(const ml2048_prepare_args &a, cudaStream_t s)
+{
+    static int max_blocks[2] = {0, 0};  // co-resident blocks on this device, per rng mode (one device per process)
+    const int mode = a.rng_mode == ML2048_RNG_REPLAY ? 0 : 1;
+    const void *kernel = mode == 0 ? (const void *)prepare_fused_kernel<ML2048_RNG_REPLAY> : (const void *)prepare_fused_kernel<ML2048_RNG_PHILOX>;
+    if (max_blocks[mode] == 0) {
+        int dev = 0, sms = 0, per_sm = 0, coop = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPrepThreads, 0);
+        if (e != cudaSuccess) return (int)e;
+        max_blocks[mode] = coop ? sms * per_sm : -1;
+    }
+    if (max_blocks[mode] <= 0) return ML2048_E_SIZE;
+    const int64_t n16 = (a.num_games + 15) / 16;
+    const int64_t tiles = (a.num_games + kPrepTile - 1) / kPrepTile;  // the scratch holds one int per tile
+    const int64_t blocks = tiles < max_blocks[mode] ? tiles : max_blocks[mode];
+    if ((n16 + blocks - 1) / blocks > kFusedMaxGroups) return ML2048_E_SIZE;
+    ml2048_prepare_args args = a;
+    int32_t *counts = a.scratch;
+    void *params[] = {&args, &counts};
+    const cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3((unsigned)blocks), dim3(kPrepThreads), params, 0, s);
+    return e == cudaSuccess ? launch_status() : (int)e;
+}
+
 int ml2048_prepare(const ml2048_prepare_args *args, void *stream)
 {
     int rc = check_prepare_args(args);
@@ -918,6 +1101,12 @@ int ml2048_prepare(const ml2048_prepare_args *args, void *stream)
         else
             prepare_small_kernel<ML2048_RNG_PHILOX><<<1, kPrepThreads, 0, s>>>(*args);
         return launch_status();
+    }
+    // ML2048_PREPARE=split in the environment forces the three-launch path (A/B measurements)
+    const char *mode = getenv("ML2048_PREPARE");
+    if (!args->id_offset && !(mode && mode[0] == 's')) {
+        rc = launch_prepare_fused(*args, static_cast<cudaStream_t>(stream));
+        if (rc != ML2048_E_SIZE) return rc;  // E_SIZE: the batch does not fit the single-wave kernel, use three launches
     }
     rc = ml2048_prepare_count(args, stream);
     if (rc) return rc;

@@ -622,3 +622,33 @@ def test_long_soak_against_oracle(ml, oracle):
             for name, dev in (("score", env._score), ("reward", env._reward)):
                 np.testing.assert_array_equal(dev.cpu().numpy().view(np.uint32), d[name].view(np.uint32), err_msg=f"{name} at step {t}")
     assert env._game_count == ref._game_count > 80 * m
+
+
+@pytest.mark.parametrize("m,onehot", [(8193, None), (50021, "f32"), (50021, "u8"), ((1 << 20) + 3, "bf16"), ((1 << 21) + 17, None)])
+def test_single_launch_prepare_equals_three_launch_prepare(ml, m, onehot, monkeypatch):
+    """The cooperative single-launch auto-reset and the count/scan/apply path (ML2048_PREPARE=split) leave the same
+    state behind -- ids, reset index list, boards, masks, cleared fields, one-hot rows -- from a fresh reset (every
+    game is over: several list windows per block) and from the middle of a rollout (about 1 % of the games are over)."""
+    envs = {}
+    for mode in ("split", "fused"):
+        monkeypatch.setenv("ML2048_PREPARE", mode)
+        env = ml.VecGame(m, "improved", output="torch", onehot=onehot, sync_free=False)
+        env.reset(5)
+        seen = []
+        for t in range(70):
+            (idx,) = env.prepare()
+            if t in (0, 1, 40, 69):
+                seen.append(idx.clone())
+            env.step_random()
+        (idx,) = env.prepare()
+        seen.append(idx.clone())
+        envs[mode] = (env, seen)
+    (a, ia), (b, ib) = envs["split"], envs["fused"]
+    for x, y in zip(ia, ib):
+        assert torch.equal(x, y)
+    assert len(ia[0]) == m and 0 < len(ia[-1]) < m // 20
+    assert a._game_count == b._game_count
+    for name in ("_board", "_valid", "_id", "_step", "_score", "_reward", "_terminated_padded", "_invalid"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    if onehot:
+        assert torch.equal(a.observations_onehot(), b.observations_onehot())
