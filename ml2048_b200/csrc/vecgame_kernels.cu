@@ -22,7 +22,10 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kStepThreads = 256;   // games per block in the core-only step kernel and the small stand-alone ops
+#ifndef ML2048_STEP_THREADS
+#define ML2048_STEP_THREADS 256
+#endif
+constexpr int kStepThreads = ML2048_STEP_THREADS;   // games per block in the core-only step kernel and the small stand-alone ops
 // With a fused one-hot the kernel is a pure HBM write stream; larger blocks (each writing one contiguous
 // 768 KiB tile in fp32) measured 3.5 % faster than 256-thread blocks (2844 vs 2949 us at M = 2^24).
 #ifndef ML2048_ONEHOT_STEP_THREADS
@@ -212,8 +215,8 @@ __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, 
 // kFull adds the rollout extras (policy-logits sampling, transition record, episode log); the lean variant
 // compiles them out so the plain step pays nothing for them.
 template <int kRng, bool kLog, int kOneHot, bool kFull, int kThreads>
-// 256-thread blocks: 8 per SM (all 2048 thread slots) needs <= 32 registers
-__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 8 : 2) step_kernel(const ml2048_step_args a)
+// small blocks: all 2048 thread slots of an SM filled, i.e. <= 32 registers
+__global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? 2 : 2048 / kThreads) step_kernel(const ml2048_step_args a)
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kThreads : 1];
 #if defined(ML2048_ONEHOT_TMA)
@@ -1063,30 +1066,41 @@ int ml2048_prepare_apply(const ml2048_prepare_args *args, void *stream)
     return launch_status();
 }
 
-// Single-wave cooperative launch of the fused auto-reset; ML2048_E_SIZE when the batch is too large for it.
+// Single-wave cooperative launch of the fused auto-reset; ML2048_E_SIZE when the batch (or the device) does not allow it.
 static int launch_prepare_fused(const ml2048_prepare_args &a, cudaStream_t s)
 {
-    static int max_blocks[2] = {0, 0};  // co-resident blocks on this device, per rng mode (one device per process)
+    constexpr int kMaxDevices = 64;
+    static int max_blocks[kMaxDevices][2];  // co-resident blocks per device and rng mode; 0 = not asked yet, -1 = unavailable
     const int mode = a.rng_mode == ML2048_RNG_REPLAY ? 0 : 1;
     const void *kernel = mode == 0 ? (const void *)prepare_fused_kernel<ML2048_RNG_REPLAY> : (const void *)prepare_fused_kernel<ML2048_RNG_PHILOX>;
-    if (max_blocks[mode] == 0) {
-        int dev = 0, sms = 0, per_sm = 0, coop = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= kMaxDevices) return ML2048_E_SIZE;
+    int &blocks_here = max_blocks[dev][mode];
+    if (blocks_here == 0) {
+        int sms = 0, per_sm = 0, coop = 0;
+        e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPrepThreads, 0);
         if (e != cudaSuccess) return (int)e;
-        max_blocks[mode] = coop ? sms * per_sm : -1;
+        blocks_here = coop && sms * per_sm > 0 ? sms * per_sm : -1;
     }
-    if (max_blocks[mode] <= 0) return ML2048_E_SIZE;
+    if (blocks_here <= 0) return ML2048_E_SIZE;
     const int64_t n16 = (a.num_games + 15) / 16;
     const int64_t tiles = (a.num_games + kPrepTile - 1) / kPrepTile;  // the scratch holds one int per tile
-    const int64_t blocks = tiles < max_blocks[mode] ? tiles : max_blocks[mode];
+    const int64_t blocks = tiles < blocks_here ? tiles : blocks_here;
     if ((n16 + blocks - 1) / blocks > kFusedMaxGroups) return ML2048_E_SIZE;
     ml2048_prepare_args args = a;
     int32_t *counts = a.scratch;
     void *params[] = {&args, &counts};
-    const cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3((unsigned)blocks), dim3(kPrepThreads), params, 0, s);
+    e = cudaLaunchCooperativeKernel(kernel, dim3((unsigned)blocks), dim3(kPrepThreads), params, 0, s);
+    if (e == cudaErrorCooperativeLaunchTooLarge) {
+        // fewer SMs are available to this context than the device reports (MPS share, green context): three launches
+        (void)cudaGetLastError();
+        blocks_here = -1;
+        return ML2048_E_SIZE;
+    }
     return e == cudaSuccess ? launch_status() : (int)e;
 }
 
