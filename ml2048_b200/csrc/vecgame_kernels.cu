@@ -32,6 +32,13 @@ constexpr int kStepThreads = ML2048_STEP_THREADS;   // games per block in the co
 #define ML2048_ONEHOT_STEP_THREADS 768
 #endif
 constexpr int kOneHotStepThreads = ML2048_ONEHOT_STEP_THREADS;
+// Small batches with a fused one-hot (the training shape, M = 2048..4096) are latency-bound: smaller blocks spread the
+// one-hot rows over more SMs.
+#ifndef ML2048_SMALL_STEP_THREADS
+#define ML2048_SMALL_STEP_THREADS 64
+#endif
+constexpr int kSmallStepThreads = ML2048_SMALL_STEP_THREADS;
+constexpr int64_t kSmallStepMaxGames = 32768;
 constexpr int kPrepThreads = 256;   // threads per block in the auto-reset kernels
 constexpr int kPrepTile = kPrepThreads * 16;  // games per block there (16 terminated flags per thread)
 constexpr int kRandRows = 1024;     // VecGame._RAND_SIZE, game_numba.py:533
@@ -216,7 +223,7 @@ __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, 
 // compiles them out so the plain step pays nothing for them.
 template <int kRng, bool kLog, int kOneHot, bool kFull, int kThreads>
 // small blocks: all 2048 thread slots of an SM filled, i.e. <= 32 registers
-__global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? 2 : 2048 / kThreads) step_kernel(const ml2048_step_args a)
+__global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? 2 : (2048 / kThreads > 32 ? 32 : 2048 / kThreads)) step_kernel(const ml2048_step_args a)
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kThreads : 1];
 #if defined(ML2048_ONEHOT_TMA)
@@ -899,12 +906,16 @@ inline int launch_status()
 template <int kRng, bool kLog, bool kFull>
 int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
 {
-    // large batches: 768-thread blocks (one contiguous 768 KiB fp32 tile each); small batches need the parallelism
-    // of many 256-thread blocks (M = 2048 is 8 blocks instead of 3)
+    // large batches: 768-thread blocks (one contiguous 768 KiB fp32 tile each); medium batches 256-thread blocks; small
+    // batches (the training shape) 64-thread blocks, so that the one-hot rows are written by many SMs: M = 2048 is 32
+    // blocks instead of 8 (or 3)
     constexpr int T = kOneHotStepThreads;
+    constexpr int S = kSmallStepThreads;
     const bool big = a.num_games >= (1 << 19);
+    const bool small = a.num_games <= kSmallStepMaxGames;
     const unsigned grid = (unsigned)((a.num_games + kStepThreads - 1) / kStepThreads);
     const unsigned grid_big = (unsigned)((a.num_games + T - 1) / T);
+    const unsigned grid_small = (unsigned)((a.num_games + S - 1) / S);
     const int onehot = a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE;
     if (onehot < ML2048_ONEHOT_NONE || onehot > ML2048_ONEHOT_U8) return ML2048_E_ENUM;
 #if defined(ML2048_ONEHOT_TMA)
@@ -919,10 +930,12 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
             opted_in = true;                                                                           \
         }                                                                                              \
         step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, smem, s>>>(a);                             \
-    } else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
+    } else if (small) step_kernel<kRng, kLog, OH, kFull, S><<<grid_small, S, 0, s>>>(a);                \
+    else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
 #else
 #define ML2048_LAUNCH(OH)                                                                              \
     if (big) step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, 0, s>>>(a);                           \
+    else if (small) step_kernel<kRng, kLog, OH, kFull, S><<<grid_small, S, 0, s>>>(a);                  \
     else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
 #endif
     switch (onehot) {
