@@ -32,6 +32,10 @@ constexpr int kStepThreads = ML2048_STEP_THREADS;   // games per block in the co
 #define ML2048_ONEHOT_STEP_THREADS 768
 #endif
 constexpr int kOneHotStepThreads = ML2048_ONEHOT_STEP_THREADS;
+#ifndef ML2048_ONEHOT_STEP_MIN_BLOCKS
+#define ML2048_ONEHOT_STEP_MIN_BLOCKS 2
+#endif
+constexpr int kOneHotStepMinBlocks = ML2048_ONEHOT_STEP_MIN_BLOCKS;  // resident blocks per SM the large-batch kernel is compiled for
 // Small batches with a fused one-hot (the training shape, M = 2048..4096) are latency-bound: smaller blocks spread the
 // one-hot rows over more SMs.
 #ifndef ML2048_SMALL_STEP_THREADS
@@ -223,7 +227,7 @@ __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, 
 // compiles them out so the plain step pays nothing for them.
 template <int kRng, bool kLog, int kOneHot, bool kFull, int kThreads>
 // small blocks: all 2048 thread slots of an SM filled, i.e. <= 32 registers
-__global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? 2 : (2048 / kThreads > 32 ? 32 : 2048 / kThreads)) step_kernel(const ml2048_step_args a)
+__global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOneHotStepMinBlocks : (2048 / kThreads > 32 ? 32 : 2048 / kThreads)) step_kernel(const ml2048_step_args a)
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kThreads : 1];
 #if defined(ML2048_ONEHOT_TMA)
@@ -257,14 +261,24 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? 2 :
             rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)philox_counter,
                                 (uint32_t)(philox_counter >> 32), (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
         uint32_t action;
+        // The current mask is a function of the current board.  The variants with a fused one-hot are HBM-bound with
+        // idle issue slots, and every extra READ stream costs a write-dominated kernel far more than its bytes (DRAM bus
+        // turnarounds: tools/write_patterns.cu), so they recompute the mask (~45 instructions) instead of loading it; the
+        // issue-bound core-only kernel loads it.
+        const auto current_mask = [&]() -> uint32_t {
+#if !defined(ML2048_LOAD_MASK)
+            if (kOneHot != ML2048_ONEHOT_NONE) return valid_mask(bd.x, bd.y, bd.z, bd.w);
+#endif
+            return reinterpret_cast<const uint32_t *>(a.valid_in)[g];
+        };
         if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
             // uniform over the valid directions (policy/random.py:17-27); 0 when the game is over
-            const uint32_t bits = mask_bits4(reinterpret_cast<const uint32_t *>(a.valid_in)[g]);
+            const uint32_t bits = mask_bits4(current_mask());
             const uint32_t nv = popc32(bits);
             action = nv ? kth_valid_action(bits, umulhi32(rnd.z, nv)) : 0u;
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
         } else if (kFull && a.action_mode == ML2048_ACTIONS_FROM_LOGITS) {
-            const uint32_t bits = mask_bits4(reinterpret_cast<const uint32_t *>(a.valid_in)[g]);
+            const uint32_t bits = mask_bits4(current_mask());
             const float4 lg = reinterpret_cast<const float4 *>(a.logits)[g];
             float lp;
             action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.z, lp);
