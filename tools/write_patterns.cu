@@ -202,6 +202,64 @@ __global__ void __launch_bounds__(T) tile_tma_reads(uint4 *out, size_t n16, int 
     if (kMode == 3 && acc == 0x12345678u) sink[0] = acc;
 }
 
+// the block's inputs fetched by the TMA engine as four bulk copies (12 KiB + 3 x 3 KiB) into shared memory instead of
+// ~100 warp-level loads: does the memory system treat few large read requests more kindly inside a write stream?
+template <int T>
+__global__ void __launch_bounds__(T) tile_tma_bulkreads(uint4 *out, size_t n16, int tile16, int chunk16, const uint4 *rd16, const uint32_t *rd4,
+                                                         size_t games)
+{
+    extern __shared__ __align__(128) uint4 stage[];  // [2][chunk16] staging, then the inputs
+    __shared__ __align__(8) unsigned long long bar;
+    uint4 *in16 = stage + 2 * chunk16;
+    uint32_t *in4 = reinterpret_cast<uint32_t *>(in16 + T);
+    const size_t g0 = (size_t)blockIdx.x * T;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = T * 16 + 3 * T * 4;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(total) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(in16)),
+                     "l"(rd16 + g0), "r"((uint32_t)(T * 16)), "r"(bar_a)
+                     : "memory");
+        for (int k = 0; k < 3; ++k)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(in4 + k * T)),
+                         "l"(rd4 + k * games + g0), "r"((uint32_t)(T * 4)), "r"(bar_a)
+                         : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_a) : "memory");
+    }
+    const uint4 b = in16[threadIdx.x];
+    uint4 v = make_uint4(0x3f800000u, b.x ^ b.y ^ b.z ^ b.w ^ in4[threadIdx.x] ^ in4[T + threadIdx.x] ^ in4[2 * T + threadIdx.x], 0, 0x3f800000u);
+    char *base = reinterpret_cast<char *>(out + (size_t)blockIdx.x * tile16);
+    int buf = 0;
+    for (int c0 = 0; c0 < tile16; c0 += chunk16, buf ^= 1) {
+        uint4 *dst = stage + buf * chunk16;
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        for (int i = threadIdx.x; i < chunk16; i += T) dst[i] = v;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + (size_t)c0 * 16), "r"(src),
+                         "r"((uint32_t)chunk16 * 16u)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+}
+
 template <class F>
 static float timed(F launch, int reps = 6)
 {
@@ -283,6 +341,8 @@ int main()
         report("tile_tma 768 + reads via ld.global.cg", timed([&] { tile_tma_reads<768, 2><<<grid, 768, 2 * 49152>>>(out, n16, 768 * 64, 3072, rd16, rd4, games, wr4); }));
         report("tile_tma 768 + reads (nc) not feeding the tile", timed([&] { tile_tma_reads<768, 3><<<grid, 768, 2 * 49152>>>(out, n16, 768 * 64, 3072, rd16, rd4, games, wr4); }));
         report("tile_tma 768 + reads via ld.global.nc", timed([&] { tile_tma_reads<768, 4><<<grid, 768, 2 * 49152>>>(out, n16, 768 * 64, 3072, rd16, rd4, games, wr4); }));
+        CK(cudaFuncSetAttribute(tile_tma_bulkreads<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 49152 + 768 * 28));
+        report("tile_tma 768 + the reads as four TMA bulk loads per block", timed([&] { tile_tma_bulkreads<768><<<grid, 768, 2 * 49152 + 768 * 28>>>(out, n16, 768 * 64, 3072, rd16, rd4, games); }));
         CK(cudaFuncSetAttribute(tile_tma_pipelined<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 49152));
         for (int tiles : {1, 2, 37, 74})
         {
