@@ -324,7 +324,9 @@ int main()
         CK(cudaFuncSetAttribute(tile_tma_mixed<768, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 49152));
         CK(cudaFuncSetAttribute(tile_tma_mixed<768, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 49152));
         report("tile_tma 768 + 28 B/game reads", timed([&] { tile_tma_mixed<768, true, false><<<grid, 768, 2 * 49152>>>(out, n16, 768 * 64, 3072, rd16, rd4, wr16, wr4, wr1, games); }));
-        report("tile_tma 768 + reads from a 1 Mi-game window (L2-resident)", timed([&] { tile_tma_mixed<768, true, false><<<grid, 768, 2 * 49152>>>(out, n16, 768 * 64, 3072, rd16, rd4, wr16, wr4, wr1, games, (1u << 20) - 1, 0); }));
+        report("tile_tma 768 + reads from a 1 Mi-game window (28 MB, re-read every 160 us)", timed([&] { tile_tma_mixed<768, true, false><<<grid, 768, 2 * 49152>>>(out, n16, 768 * 64, 3072, rd16, rd4, wr16, wr4, wr1, games, (1u << 20) - 1, 0); }));
+        report("tile_tma 768 + reads from a 64 Ki-game window (1.8 MB, re-read every 10 us)", timed([&] { tile_tma_mixed<768, true, false><<<grid, 768, 2 * 49152>>>(out, n16, 768 * 64, 3072, rd16, rd4, wr16, wr4, wr1, games, (1u << 16) - 1, 0); }));
+        report("tile_tma 768 + reads from a 4 Ki-game window (115 KB, always in L2)", timed([&] { tile_tma_mixed<768, true, false><<<grid, 768, 2 * 49152>>>(out, n16, 768 * 64, 3072, rd16, rd4, wr16, wr4, wr1, games, (1u << 12) - 1, 0); }));
         for (int ahead : {296, 600, 1200, 2400})
         {
             char name[96];
