@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ML2048_ABI_VERSION 7
+#define ML2048_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define ML2048_API __attribute__((visibility("default")))
@@ -115,8 +115,12 @@ typedef struct {
     const void *actions;   /* [num_games] of action_dtype, values 0..3 (others count as invalid moves) */
     void *actions_out;     /* [num_games] u8 or null: the action chosen in-kernel (RANDOM_VALID, FROM_LOGITS) */
 
-    int32_t *step;         /* in place; += 1 on a valid move            (game_numba.py:719) */
-    float *score;          /* in place; += normal reward on a valid move (:729-731) */
+    int32_t *step;         /* in place; += 1 on a valid move            (game_numba.py:719).  `step` and `score` are the halves of ONE
+                              array of 8-byte {int32 step, float score} records, [num_games][2] words: step[2*g] and
+                              score[2*g] belong to game g, score == (float *)step + 1, step 8-byte aligned (else ML2048_E_ALIGN).
+                              One load and one store per game instead of two of each: a write-dominated kernel pays for
+                              every separate read stream (profiles/README.md). */
+    float *score;          /* in place; += normal reward on a valid move (:729-731); see `step` */
     float *reward;         /* in place; written on a valid move only: stays stale otherwise (:730, :737-738) */
     uint8_t *terminated;   /* in place; written on a valid move only (:735) */
     uint8_t *invalid;      /* always written (:736, :738) */
@@ -198,7 +202,7 @@ typedef struct {
     void *board;           /* [num_games][16] */
     void *valid;           /* [num_games][4] */
     int32_t *id;           /* [num_games] (game_numba.py:641-644) */
-    int32_t *step;
+    int32_t *step;         /* {step, score} records, as in ml2048_step_args */
     float *score;
     float *reward;
     uint8_t *terminated;   /* [ceil16(num_games)] : padded to a multiple of 16 bytes, padding zero */

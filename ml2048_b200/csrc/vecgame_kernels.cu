@@ -317,8 +317,11 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
             } else {
                 reward = (float)gain;
             }
-                        const float score = a.score[g] + (float)gain;
-            const int32_t nstep = a.step[g] + 1;
+                        // step count and score are the halves of ONE 8-byte record per game: one load, one store, one stream
+            int2 *const step_score = reinterpret_cast<int2 *>(a.step) + g;
+            const int2 old_ss = *step_score;
+            const float score = __int_as_float(old_ss.y) + (float)gain;
+            const int32_t nstep = old_ss.x + 1;
 
             // spawn one tile (_spawn2 with count = 1, game_numba.py:733)
             const uint32_t n0 = occupied_signs(r0), n1 = occupied_signs(r1), n2 = occupied_signs(r2), n3 = occupied_signs(r3);
@@ -342,8 +345,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
             const bool dead = vm == 0u;
             reinterpret_cast<uint32_t *>(a.valid_out)[g] = vm;
             a.reward[g] = reward;
-            a.score[g] = score;
-            a.step[g] = nstep;
+            *step_score = make_int2(nstep, __float_as_int(score));
             a.terminated[g] = dead ? 1 : 0;
             a.invalid[g] = 0;
             if (kLog) {
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
             a.invalid[g] = 1;
             if (kFull) {  // stale values are recorded stale (run_train3.py:146-148)
                 if (a.tr_reward) tr_reward = a.reward[g];
-                if (a.tr_step) tr_step = a.step[g];
+                if (a.tr_step) tr_step = a.step[2 * g];
                 if (a.tr_terminated) tr_term = a.terminated[g];
             }
         }
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
             const int64_t e = (int64_t)a.id[g] - a.traj_id_base;
             if (!was_over && e >= 0 && e < a.traj_capacity) {
                 const bool dead_now = moved && tr_term;
-                const float sc = moved ? tr_score : a.score[g];  // after this step (stale on an invalid move, like result["score"])
+                const float sc = moved ? tr_score : a.score[2 * g];  // after this step (stale on an invalid move, like result["score"])
                 if (row < a.traj_max_rows) {
                     const int64_t k = e * a.traj_max_rows + row;
                     reinterpret_cast<uint4 *>(a.traj_state)[k] = bd;
@@ -560,8 +562,7 @@ __device__ __forceinline__ uint4 reset_slot(const ml2048_prepare_args &a, const 
     reinterpret_cast<uint4 *>(a.board)[g] = bd;
     reinterpret_cast<uint32_t *>(a.valid)[g] = valid_mask(r0, r1, r2, r3);
     a.id[g] = (int32_t)(id_base + order);
-    a.step[g] = 0;
-    a.score[g] = 0.0f;
+    reinterpret_cast<int2 *>(a.step)[g] = make_int2(0, 0);  // step = 0, score = 0.0f: one store
     a.reward[g] = 0.0f;
     a.invalid[g] = 0;
     if (a.merged) reinterpret_cast<uint4 *>(a.merged)[g] = make_uint4(0, 0, 0, 0);
@@ -911,6 +912,12 @@ __global__ void fill_terminated_kernel(uint8_t *terminated, int64_t num_games, i
 
 inline bool misaligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
 
+// `step` and `score` must be the two halves of one array of 8-byte {int32 step, float score} records
+inline bool not_a_step_score_pair(const int32_t *step, const float *score)
+{
+    return misaligned(step, 8) || reinterpret_cast<const char *>(score) != reinterpret_cast<const char *>(step) + 4;
+}
+
 inline int launch_status()
 {
     const cudaError_t e = cudaGetLastError();
@@ -995,6 +1002,7 @@ int ml2048_step(const ml2048_step_args *args, void *stream)
     if (!a.board_in || !a.board_out || !a.valid_out || !a.step || !a.score || !a.reward || !a.terminated || !a.invalid)
         return ML2048_E_NULL;
     if (a.board_in == a.board_out) return ML2048_E_NULL;
+    if (not_a_step_score_pair(a.step, a.score)) return ML2048_E_ALIGN;
     if (misaligned(a.board_in, 16) || misaligned(a.board_out, 16) || misaligned(a.valid_out, 4) || misaligned(a.merged, 16) ||
         misaligned(a.onehot_out, 16) || misaligned(a.valid_in, 4) || misaligned(a.stats, 8))
         return ML2048_E_ALIGN;
@@ -1046,6 +1054,7 @@ static int check_prepare_args(const ml2048_prepare_args *args)
     if (!a.board || !a.valid || !a.id || !a.step || !a.score || !a.reward || !a.terminated || !a.invalid || !a.game_count ||
         !a.reset_count || !a.scratch)
         return ML2048_E_NULL;
+    if (not_a_step_score_pair(a.step, a.score)) return ML2048_E_ALIGN;
     if (misaligned(a.board, 16) || misaligned(a.valid, 4) || misaligned(a.terminated, 16) || misaligned(a.merged, 16) ||
         misaligned(a.onehot, 16) || misaligned(a.randperm, 16) || misaligned(a.scratch, 8) || misaligned(a.game_count, 8) ||
         misaligned(a.reset_count, 8) || misaligned(a.reset_indices, 8) || misaligned(a.id_offset, 8))
@@ -1162,8 +1171,9 @@ int ml2048_reset_state(void *board_a, void *board_b, void *valid_a, void *valid_
         return ML2048_E_NULL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)num_games;
+    if (not_a_step_score_pair(step, score)) return ML2048_E_ALIGN;
     const struct { void *p; size_t bytes; } clears[] = {{board_a, n * 16}, {board_b, n * 16}, {valid_a, n * 4}, {valid_b, n * 4},
-                                                        {id, n * 4},       {step, n * 4},     {score, n * 4},   {reward, n * 4},
+                                                        {id, n * 4},       {step, n * 8} /* {step, score} pairs */, {reward, n * 4},
                                                         {invalid, n},      {merged, n * 16}};
     for (const auto &c : clears) {
         if (!c.p) continue;

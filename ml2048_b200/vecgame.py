@@ -212,8 +212,9 @@ class VecGame:
             # that the NumPy drop-in mode can mirror it to the host with a single copy (see _mirror_to_host).
             layout = [("_reset_count_dev", torch.int64, (1,)), ("_game_count_dev", torch.int64, (1,)),  # count survives reset(), :582
                       ("_reset_indices_dev", torch.int64, (m,)), ("_board", torch.uint8, (2, m, 16)),
-                      ("_valid", torch.uint8, (2, m, 4)), ("_id", torch.int32, (m,)), ("_step", torch.int32, (m,)),
-                      ("_score", torch.float32, (m,)), ("_reward", torch.float32, (m,)),
+                      ("_valid", torch.uint8, (2, m, 4)), ("_id", torch.int32, (m,)),
+                      ("_step_score", torch.int32, (m, 2)),  # {step, score} records: one stream for the kernels (ml2048_b200.h)
+                      ("_reward", torch.float32, (m,)),
                       ("_terminated_padded", torch.uint8, (pad,)), ("_invalid", torch.uint8, (m,))]
             if track_merged:
                 layout.append(("_merged", torch.uint8, (m, 16)))
@@ -228,6 +229,9 @@ class VecGame:
             for name, (off, nbytes, dtype, shape) in offsets.items():
                 setattr(self, name, self._arena[off:off + nbytes].view(dtype).view(shape))
             self._terminated = self._terminated_padded[:m]
+            # strided views of the records, like the reference's own views into its record array (game_numba.py:687-698)
+            self._step = self._step_score[:, 0]
+            self._score = self._step_score[:, 1].view(torch.float32)
             if not track_merged:
                 self._merged = None
             self._onehot = torch.zeros((m, 16, 16), dtype=onehot_dtype, device=dev) if onehot_dtype is not None else None
@@ -389,6 +393,8 @@ class VecGame:
             for name, (off, nbytes, dtype, shape) in self._arena_layout.items():
                 npdt = {torch.int64: np.int64, torch.int32: np.int32, torch.float32: np.float32, torch.uint8: np.uint8}[dtype]
                 views[name] = flat[off:off + nbytes].view(npdt).reshape(shape)
+            views["_step"] = views["_step_score"][:, 0]
+            views["_score"] = views["_step_score"][:, 1].view(np.float32)
             self._mirror = views
         self._arena_host.copy_(self._arena, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
@@ -900,8 +906,8 @@ class VecGame:
                 a.valid_in = self._valid_ptr[cur] + 4 * lo
                 a.valid_out = self._valid_ptr[1 - cur] + 4 * lo
                 a.actions = dev_actions.data_ptr() + esz * lo
-                a.step = self._step.data_ptr() + 4 * lo
-                a.score = self._score.data_ptr() + 4 * lo
+                a.step = self._step.data_ptr() + 8 * lo   # {step, score} records
+                a.score = self._score.data_ptr() + 8 * lo
                 a.reward = self._reward.data_ptr() + 4 * lo
                 a.terminated = self._terminated_padded.data_ptr() + lo
                 a.invalid = self._invalid.data_ptr() + lo
@@ -956,7 +962,7 @@ class VecGame:
         torch.cuda.current_stream(self.device).synchronize()
         tensors = {
             name: getattr(self, name).clone()
-            for name in ("_board", "_valid", "_id", "_step", "_score", "_reward", "_terminated_padded", "_invalid",
+            for name in ("_board", "_valid", "_id", "_step_score", "_reward", "_terminated_padded", "_invalid",
                          "_tables_dev", "_game_count_dev", "_stats_dev")
         }
         if self._merged is not None:

@@ -69,6 +69,13 @@ def test_argument_errors_without_gpu(lib):
     assert lib.ml2048_step(ctypes.byref(a), None) == -3  # num_games == 0
     a.num_games = 8
     assert lib.ml2048_step(ctypes.byref(a), None) == -1  # null boards
+    # step and score must be the halves of one array of 8-byte {step, score} records (checked before anything is launched)
+    a.board_in, a.board_out, a.valid_out = 0x10000, 0x20000, 0x30000
+    a.reward, a.terminated, a.invalid = 0x40000, 0x50000, 0x60000
+    a.step, a.score = 0x70000, 0x80000
+    assert lib.ml2048_step(ctypes.byref(a), None) == -2
+    a.step, a.score = 0x70004, 0x70008
+    assert lib.ml2048_step(ctypes.byref(a), None) == -2  # records are 8-byte aligned
     assert lib.ml2048_prepare_scratch_ints(0) == 0
     assert lib.ml2048_prepare_scratch_ints(4096) == 4
     assert lib.ml2048_prepare_scratch_ints(4097) == 4

@@ -50,8 +50,10 @@ def test_kernels_stay_inside_their_buffers(m, onehot):
     ar = Arena(m * (16 * 3 + 4 * 2 + 4 * 4 + 2 + 8 + 4 + 256 * esz + 50 + 16 + 4) + pad + 40 * GAP + (1 << 20))
     board = [ar.take(16 * m), ar.take(16 * m)]
     valid = [ar.take(4 * m), ar.take(4 * m)]
-    ids, step = ar.take(4 * m, torch.int32), ar.take(4 * m, torch.int32)
-    score, reward = ar.take(4 * m, torch.float32), ar.take(4 * m, torch.float32)
+    ids, reward = ar.take(4 * m, torch.int32), ar.take(4 * m, torch.float32)
+    step_score = ar.take(8 * m, torch.int32)  # {step, score} records (ml2048_b200.h)
+    step_ptr, score_ptr = step_score.data_ptr(), step_score.data_ptr() + 4
+    score = step_score.view(m, 2)[:, 1].view(torch.float32)
     term, invalid = ar.take(pad, fill=0), ar.take(m)
     term[:m] = 1
     merged = ar.take(16 * m)
@@ -79,13 +81,13 @@ def test_kernels_stay_inside_their_buffers(m, onehot):
     ref.reset(9)
 
     p = _lib.PrepareArgs(struct_size=C.sizeof(_lib.PrepareArgs), rng_mode=_lib.RNG_PHILOX, onehot_dtype=onehot, num_games=m, slot_base=0,
-                         id=ids.data_ptr(), step=step.data_ptr(), score=score.data_ptr(), reward=reward.data_ptr(),
+                         id=ids.data_ptr(), step=step_ptr, score=score_ptr, reward=reward.data_ptr(),
                          terminated=term.data_ptr(), invalid=invalid.data_ptr(), merged=merged.data_ptr(),
                          onehot=oh.data_ptr() if onehot else None, randperm=tables.data_ptr(), two_mask=0xFFFF,
                          two_threshold=ref._two_threshold, philox_seed=ref._philox_seed, game_count=game_count.data_ptr(),
                          reset_count=reset_count.data_ptr(), reset_indices=indices.data_ptr(), scratch=scratch.data_ptr())
     a = _lib.StepArgs(struct_size=C.sizeof(_lib.StepArgs), reward_kind=0, rng_mode=_lib.RNG_PHILOX, onehot_dtype=onehot, num_games=m,
-                      slot_base=0, step=step.data_ptr(), score=score.data_ptr(), reward=reward.data_ptr(), terminated=term.data_ptr(),
+                      slot_base=0, step=step_ptr, score=score_ptr, reward=reward.data_ptr(), terminated=term.data_ptr(),
                       invalid=invalid.data_ptr(), merged=merged.data_ptr(), onehot_out=oh.data_ptr() if onehot else None,
                       randperm_keys=tables.data_ptr() + 16384, two_mask=0xFFFF, two_threshold=ref._two_threshold,
                       philox_seed=ref._philox_seed, stats=stats.data_ptr(), actions_out=actions_out.data_ptr(),
