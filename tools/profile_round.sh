@@ -8,5 +8,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 100 --csv --
 # 3. full capture of the fused step kernel and of the fused prepare kernel (steady state)
 ncu --set full --clock-control none --import-source on -k regex:"step_kernel|prepare_fused" -s 516 -c 2 -o gpurun_out/prof_step_r01_g -f python bench.py --steps 3 --warmup 3 --burn-in 256 --no-e2e --no-extras --no-cpu-baseline > gpurun_out/ncu_step_r01_g.log 2>&1
 # 4. full capture of the core-only step kernel with given actions
-ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 264 -c 1 -o gpurun_out/prof_core_given_r01_e -f python tools/profile_core.py --steps 6 --burn-in 256 --actions given > gpurun_out/ncu_core_r01_e.log 2>&1
-tail -n 2 gpurun_out/ncu_step_r01_g.log; tail -n 2 gpurun_out/ncu_core_r01_e.log
+ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 264 -c 1 -o gpurun_out/prof_core_given_r01_g -f python tools/profile_core.py --steps 6 --burn-in 256 --actions given > gpurun_out/ncu_core_r01_g.log 2>&1
+tail -n 2 gpurun_out/ncu_step_r01_g.log; tail -n 2 gpurun_out/ncu_core_r01_g.log
