@@ -226,8 +226,12 @@ __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, 
 // kFull adds the rollout extras (policy-logits sampling, transition record, episode log); the lean variant
 // compiles them out so the plain step pays nothing for them.
 template <int kRng, bool kLog, int kOneHot, bool kFull, int kThreads>
-// small blocks: all 2048 thread slots of an SM filled, i.e. <= 32 registers
-__global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOneHotStepMinBlocks : (2048 / kThreads > 32 ? 32 : 2048 / kThreads)) step_kernel(const ml2048_step_args a)
+// lean variants in small blocks: all 2048 thread slots of an SM filled, i.e. <= 32 registers; the variants with the rollout
+// extras hold more live values and are left to the register allocator (no spills)
+__global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOneHotStepMinBlocks
+                                            : kFull                         ? 1
+                                                                            : (2048 / kThreads > 32 ? 32 : 2048 / kThreads))
+    step_kernel(const ml2048_step_args a)
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kThreads : 1];
 #if defined(ML2048_ONEHOT_TMA)
