@@ -878,17 +878,22 @@ __global__ void __launch_bounds__(kStepThreads) gae_kernel(const float *v0, cons
     const int64_t u = i / game_count, g = i - u * game_count;
     const int64_t base = u * step_count * game_count + g;
     float tmp = 0.0f;
-    // the loads do not depend on the running value: fetch four steps at a time so that several rows are in flight
+    // the loads do not depend on the running value: fetch eight steps at a time so that many rows are in flight
+    // (measured at (2, 64, 2^20): 2 ahead 890 us, 4 ahead 418 us, 8 ahead 357 us = 6.39 TB/s, 16 ahead 359 us)
     int64_t t = step_count - 1;
-    for (; t >= 3; t -= 4) {
-        float a0[4], a1[4], rw[4], mk[4];
+#ifndef ML2048_GAE_AHEAD
+#define ML2048_GAE_AHEAD 8
+#endif
+    constexpr int kAhead = ML2048_GAE_AHEAD;
+    for (; t >= kAhead - 1; t -= kAhead) {
+        float a0[kAhead], a1[kAhead], rw[kAhead], mk[kAhead];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kAhead; ++j) {
             const int64_t k = base + (t - j) * game_count;
             a0[j] = v0[k], a1[j] = v1[k], rw[j] = reward[k], mk[j] = terminated[k] ? 0.0f : 1.0f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kAhead; ++j) {
             // delta = gamma * v1 * mask + reward - v0, evaluated left to right in fp32
             const float delta = __fsub_rn(__fadd_rn(__fmul_rn(__fmul_rn(gamma, a1[j]), mk[j]), rw[j]), a0[j]);
             tmp = __fmul_rn(tmp, coef);
