@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ML2048_ABI_VERSION 8
+#define ML2048_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define ML2048_API __attribute__((visibility("default")))
@@ -132,10 +132,13 @@ typedef struct {
     const uint8_t *randperm_keys; /* [1024][16]: the reference's randperm table in inverse form,
                                      keys[row][cell] = 16*rank(cell)+cell (ml2048_pack_randperm_keys) */
     int64_t rand_seed;       /* _rand_step + rand_offset (:681); row = (rand_seed + global slot) mod 1024 */
-    uint32_t two_mask;       /* bit c set <=> (double)randfloat[c] < two_prob (see ml2048_two_mask) */
+    uint32_t two_mask;       /* bit c set <=> a tile spawned on CELL c is a 2 (else a 4).  Replay mode: (double)randfloat[c] <
+                                two_prob (ml2048_two_mask).  Philox mode: the same per-cell, per-table-epoch law drawn from the
+                                Philox stream on the host (ml2048_philox_epoch_draws) -- the reference ties the 2-vs-4 choice to
+                                the cell for a whole table epoch (game_numba.py:207), and that is part of its episode statistics */
 
     /* philox mode */
-    uint32_t two_threshold;  /* spawn a 2 iff philox word < two_threshold (see ml2048_two_threshold) */
+    uint32_t two_threshold;  /* host-side only (Bernoulli threshold of ml2048_philox_epoch_draws); the kernels ignore it */
     uint64_t philox_seed;
     uint64_t philox_counter; /* caller increments once per step */
 
@@ -287,6 +290,15 @@ ML2048_API int ml2048_gae(const float *v0, const float *v1, const float *reward,
 /* host helpers (no GPU work) */
 ML2048_API uint32_t ml2048_two_mask(const float *host_randfloat16, double two_prob);   /* game_numba.py:207 (f32 -> f64 compare) */
 ML2048_API uint32_t ml2048_two_threshold(double two_prob);
+/* Philox mode, the host half of one prepare(): the reference refreshes its spawn tables when `random() >= 0.9`
+ * (game_numba.py:622-624) and the 2-vs-4 choice then stays tied to the CELL until the next refresh (:207).  The same two
+ * draws from the counter-based stream, keyed by (seed, prepare counter) so that every shard computes identical values:
+ * *coin_u32 = a uniform 32-bit word (refresh iff >= 0.9 * 2^32), *mask16 = sixteen Bernoulli(two_prob) bits, bit c for cell c. */
+ML2048_API void ml2048_philox_epoch_draws(uint64_t philox_seed, uint64_t prepare_counter, double two_prob, uint32_t *coin_u32,
+                                          uint32_t *mask16);
+/* Philox4x32-10 and Philox2x32-10 on the host (known-answer tests; the kernels use the same rounds) */
+ML2048_API void ml2048_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+ML2048_API void ml2048_philox2x32_10(const uint32_t counter[2], uint32_t key, uint32_t out[2]);
 /* randperm (u8 [rows][16], each row a permutation of 0..15, game_numba.py:578,610) -> inverse-form keys used by
  * ml2048_step: the kernel picks the empty cell of smallest rank = the first empty cell of the table walk (:198-204) */
 ML2048_API int ml2048_pack_randperm_keys(const uint8_t *host_randperm, uint8_t *host_keys, int64_t rows);

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libml2048_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 STATS_REPLICAS = 64
 STATS_WORDS = 24  # 20 histogram bins + episodes, score_sum, step_sum, score_max (unsigned long long each)
 
@@ -157,6 +157,9 @@ SYMBOLS = {
     "ml2048_gae": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _I64, C.c_float, C.c_float, _VP]),
     "ml2048_two_mask": (_U32, [_VP, C.c_double]),
     "ml2048_two_threshold": (_U32, [C.c_double]),
+    "ml2048_philox_epoch_draws": (None, [_U64, _U64, C.c_double, C.POINTER(_U32), C.POINTER(_U32)]),
+    "ml2048_philox4x32_10": (None, [_VP, _VP, _VP]),
+    "ml2048_philox2x32_10": (None, [_VP, _U32, _VP]),
     "ml2048_pack_randperm_keys": (C.c_int, [_VP, _VP, _I64]),
     "ml2048_pcg64_random": (C.c_double, [C.POINTER(Pcg64)]),
     "ml2048_pcg64_integers": (_I64, [C.POINTER(Pcg64), _I64]),

@@ -372,6 +372,38 @@ ML2048_FN u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
     return u32x4{c0, c1, c2, c3};
 }
 
+// Philox2x32-10 (same family, Random123): two 32-bit words per block, half the multiplies and xors of Philox4x32-10.
+// A game-step consumes two uniform words -- the spawn cell (Philox mode) and the policy's action -- so this is the block
+// the kernels draw; the 4x32 variant serves the host-side epoch draws (ml2048_philox_epoch_draws).
+struct u32x2 {
+    uint32_t x, y;
+};
+
+ML2048_FN u32x2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k)
+{
+    const uint32_t M = 0xD256D193u, W = 0x9E3779B9u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi = umulhi32(M, c0), lo = M * c0;
+        c0 = hi ^ k ^ c1;
+        c1 = lo;
+        k += W;
+    }
+    return u32x2{c0, c1};
+}
+
+// The two uniform words of global slot `slot` at counter `counter` of stream `tag` (0 = step, kResetStream = auto-reset):
+// counter = (slot low word, counter low word); key = seed, the high words and the tag folded together (all but the slot's
+// high word are uniform over the launch, i.e. computed once per warp on the uniform datapath).
+constexpr uint32_t kResetStream = 0x80000000u;
+
+ML2048_FN u32x2 slot_draws(uint64_t slot, uint64_t counter, uint64_t seed, uint32_t tag)
+{
+    const uint32_t key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ ((uint32_t)(counter >> 32) * 0x85EBCA6Bu) ^
+                         ((uint32_t)(slot >> 32) * 0xC2B2AE35u) ^ tag;
+    return philox2x32_10((uint32_t)slot, (uint32_t)counter, key);
+}
+
 // Masked categorical sample (policy/actor_critic.py:56-76): invalid actions get finfo.min, the logits are
 // normalised as torch's Categorical does (x - logsumexp(x), logsumexp = max + log(sum(exp(x - max)))), one
 // uniform u in [0,1) picks the action by inverse CDF.  `mask_bits` bit k = action k valid.  Returns the action

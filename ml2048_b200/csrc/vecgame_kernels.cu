@@ -260,10 +260,9 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
     if (live) {
         const uint4 bd = reinterpret_cast<const uint4 *>(a.board_in)[g];
         const uint64_t slot = (uint64_t)(a.slot_base + g);
-        u32x4 rnd = {0u, 0u, 0u, 0u};
-        if (kRng == ML2048_RNG_PHILOX || a.action_mode != ML2048_ACTIONS_GIVEN)
-            rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)philox_counter,
-                                (uint32_t)(philox_counter >> 32), (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
+        // one Philox2x32-10 block per game-step: .x picks the spawn cell (Philox mode), .y is the policy's uniform word
+        u32x2 rnd = {0u, 0u};
+        if (kRng == ML2048_RNG_PHILOX || a.action_mode != ML2048_ACTIONS_GIVEN) rnd = slot_draws(slot, philox_counter, a.philox_seed, 0u);
         uint32_t action;
         // The current mask is a function of the current board.  The variants with a fused one-hot are HBM-bound with
         // idle issue slots, and every extra READ stream costs a write-dominated kernel far more than its bytes (DRAM bus
@@ -279,13 +278,13 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
             // uniform over the valid directions (policy/random.py:17-27); 0 when the game is over
             const uint32_t bits = mask_bits4(current_mask());
             const uint32_t nv = popc32(bits);
-            action = nv ? kth_valid_action(bits, umulhi32(rnd.z, nv)) : 0u;
+            action = nv ? kth_valid_action(bits, umulhi32(rnd.y, nv)) : 0u;
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
         } else if (kFull && a.action_mode == ML2048_ACTIONS_FROM_LOGITS) {
             const uint32_t bits = mask_bits4(current_mask());
             const float4 lg = reinterpret_cast<const float4 *>(a.logits)[g];
             float lp;
-            action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.z, lp);
+            action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.y, lp);
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
             if (a.log_prob_out) a.log_prob_out[g] = lp;
         } else {
@@ -329,20 +328,20 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
 
             // spawn one tile (_spawn2 with count = 1, game_numba.py:733)
             const uint32_t n0 = occupied_signs(r0), n1 = occupied_signs(r1), n2 = occupied_signs(r2), n3 = occupied_signs(r3);
-            uint32_t cell, value;
+            uint32_t cell;
             if (kRng == ML2048_RNG_REPLAY) {
                 const uint32_t row = (uint32_t)((uint64_t)(rand_seed + (int64_t)slot) % (uint64_t)kRandRows);
                 const uint4 keys = __ldg(reinterpret_cast<const uint4 *>(keys_table) + row);
                 // a move that changed the board leaves at least one empty cell (a slide vacates one, a fusion frees
                 // one), so the search cannot come back empty-handed here
                 cell = first_empty_key(keys.x, keys.y, keys.z, keys.w, n0, n1, n2, n3) & 15u;
-                value = 2u - ((two_mask >> cell) & 1u);
             } else {
                 const uint32_t empties = empties16(~n0 & kHi, ~n1 & kHi, ~n2 & kHi, ~n3 & kHi);
                 const uint32_t ne = popc32(empties);  // >= 1, see above
                 cell = kth_set_bit16(empties, umulhi32(rnd.x, ne));
-                value = (rnd.y < a.two_threshold) ? 1u : 2u;
             }
+            // 2 or 4: tied to the CELL for the table epoch in force (game_numba.py:207), in both modes
+            const uint32_t value = 2u - ((two_mask >> cell) & 1u);
             put_cell(r0, r1, r2, r3, cell, value);
 
             const uint32_t vm = valid_mask(r0, r1, r2, r3);
@@ -550,14 +549,13 @@ __device__ __forceinline__ uint4 reset_slot(const ml2048_prepare_args &a, const 
         v0 = 2u - ((d.two_mask >> (c0 & 15u)) & 1u);
         v1 = 2u - ((d.two_mask >> (c1 & 15u)) & 1u);
     } else {
-        const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)d.philox_counter,
-                                        (uint32_t)(d.philox_counter >> 32) ^ 0x80000000u, (uint32_t)a.philox_seed,
-                                        (uint32_t)(a.philox_seed >> 32));
+        // two distinct uniform cells; values by the epoch's per-cell mask, like the reference's reset (:648-655 with :207)
+        const u32x2 rnd = slot_draws(slot, d.philox_counter, a.philox_seed, kResetStream);
         c0 = rnd.x >> 28;
         c1 = umulhi32(rnd.y, 15u);
         c1 += (c1 >= c0) ? 1u : 0u;
-        v0 = (rnd.z < a.two_threshold) ? 1u : 2u;
-        v1 = (rnd.w < a.two_threshold) ? 1u : 2u;
+        v0 = 2u - ((d.two_mask >> c0) & 1u);
+        v1 = 2u - ((d.two_mask >> c1) & 1u);
     }
     uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u;
     put_cell(r0, r1, r2, r3, c0 & 15u, v0);
@@ -841,11 +839,10 @@ __global__ void __launch_bounds__(kStepThreads) sample_random_valid_kernel(const
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= num_games) return;
     const uint64_t slot = (uint64_t)(slot_base + g);
-    const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)counter, (uint32_t)(counter >> 32),
-                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    const u32x2 rnd = slot_draws(slot, counter, seed, 0u);  // the same policy word the step kernel draws
     const uint32_t bits = mask_bits4(valid[g]);
     const uint32_t nv = popc32(bits);
-    actions[g] = (uint8_t)(nv ? kth_valid_action(bits, umulhi32(rnd.z, nv)) : 0u);
+    actions[g] = (uint8_t)(nv ? kth_valid_action(bits, umulhi32(rnd.y, nv)) : 0u);
 }
 
 __global__ void __launch_bounds__(kStepThreads) sample_categorical_kernel(const float4 *logits, const uint32_t *valid, uint8_t *act8,
@@ -855,13 +852,12 @@ __global__ void __launch_bounds__(kStepThreads) sample_categorical_kernel(const 
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= num_games) return;
     const uint64_t slot = (uint64_t)(slot_base + g);
-    const u32x4 rnd = philox4x32_10((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)counter, (uint32_t)(counter >> 32),
-                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    const u32x2 rnd = slot_draws(slot, counter, seed, 0u);  // the same policy word the step kernel draws
     const uint32_t vm = valid[g];
     const uint32_t bits = ((vm & 0xffu) ? 1u : 0u) | ((vm & 0xff00u) ? 2u : 0u) | ((vm & 0xff0000u) ? 4u : 0u) | ((vm & 0xff000000u) ? 8u : 0u);
     const float4 lg = logits[g];
     float lp;
-    const uint32_t action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.z, lp);
+    const uint32_t action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.y, lp);
     if (act8) act8[g] = (uint8_t)action;
     if (act64) act64[g] = (long long)action;
     if (log_prob) log_prob[g] = lp;
@@ -927,10 +923,25 @@ inline bool not_a_step_score_pair(const int32_t *step, const float *score)
     return misaligned(step, 8) || reinterpret_cast<const char *>(score) != reinterpret_cast<const char *>(step) + 4;
 }
 
+// cudaGetLastError() reports AND clears the thread's sticky launch error, whoever left it there (torch, another library).
+// Every entry point therefore discards what was pending before its first launch (clear_stale_error) and checks after
+// EACH of its own launches (launch_status), so that a non-zero return always names a launch of this library.
+inline void clear_stale_error() { (void)cudaGetLastError(); }
+
 inline int launch_status()
 {
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
+}
+
+constexpr int kMaxDevices = 64;
+
+// index of the current device, or -1 (beyond the per-device tables: callers then take the uncached path)
+inline int current_device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    return (dev >= 0 && dev < kMaxDevices) ? dev : -1;
 }
 
 template <int kRng, bool kLog, bool kFull>
@@ -948,16 +959,20 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
     const unsigned grid_small = (unsigned)((a.num_games + S - 1) / S);
     const int onehot = a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE;
     if (onehot < ML2048_ONEHOT_NONE || onehot > ML2048_ONEHOT_U8) return ML2048_E_ENUM;
+    clear_stale_error();
 #if defined(ML2048_ONEHOT_TMA)
 #define ML2048_LAUNCH(OH)                                                                              \
     if (big) {                                                                                         \
         const int smem = kTmaStages * kTmaChunkBytes;                                                  \
-        static bool opted_in = false; /* > 48 KiB of dynamic shared memory needs a one-time opt-in per kernel */ \
-        if (!opted_in) {                                                                               \
+        /* > 48 KiB of dynamic shared memory needs an opt-in per kernel AND PER DEVICE (function attributes live in the \
+           device's context): one flag per device, like launch_prepare_fused's table */                \
+        static bool opted_in[kMaxDevices];                                                             \
+        const int dev_slot = current_device_slot();                                                    \
+        if (dev_slot < 0 || !opted_in[dev_slot]) {                                                     \
             const cudaError_t e = cudaFuncSetAttribute(step_kernel<kRng, kLog, OH, kFull, T>,           \
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
             if (e != cudaSuccess) return (int)e;                                                       \
-            opted_in = true;                                                                           \
+            if (dev_slot >= 0) opted_in[dev_slot] = true;                                              \
         }                                                                                              \
         step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, smem, s>>>(a);                             \
     } else if (small) step_kernel<kRng, kLog, OH, kFull, S><<<grid_small, S, 0, s>>>(a);                \
@@ -1091,7 +1106,9 @@ int ml2048_prepare_count(const ml2048_prepare_args *args, void *stream)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int64_t n16 = (a.num_games + 15) / 16;
     const int tiles = (int)((a.num_games + kPrepTile - 1) / kPrepTile);
+    clear_stale_error();
     prepare_count_kernel<<<tiles, kPrepThreads, 0, s>>>(reinterpret_cast<const uint4 *>(a.terminated), n16, a.scratch);
+    if (const int rc_count = launch_status()) return rc_count;
     prepare_scan_kernel<<<1, 1024, 0, s>>>(a.scratch, tiles, prepare_id_base_slot(a, tiles), a.game_count, a.id_offset ? 0 : 1,
                                            a.reset_count);
     return launch_status();
@@ -1104,6 +1121,7 @@ int ml2048_prepare_apply(const ml2048_prepare_args *args, void *stream)
     const ml2048_prepare_args &a = *args;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int tiles = (int)((a.num_games + kPrepTile - 1) / kPrepTile);
+    clear_stale_error();
     if (a.rng_mode == ML2048_RNG_REPLAY)
         prepare_apply_kernel<ML2048_RNG_REPLAY><<<tiles, kPrepThreads, 0, s>>>(a, a.scratch, prepare_id_base_slot(a, tiles));
     else
@@ -1114,7 +1132,6 @@ int ml2048_prepare_apply(const ml2048_prepare_args *args, void *stream)
 // Single-wave cooperative launch of the fused auto-reset; ML2048_E_SIZE when the batch (or the device) does not allow it.
 static int launch_prepare_fused(const ml2048_prepare_args &a, cudaStream_t s)
 {
-    constexpr int kMaxDevices = 64;
     static int max_blocks[kMaxDevices][2];  // co-resident blocks per device and rng mode; 0 = not asked yet, -1 = unavailable
     const int mode = a.rng_mode == ML2048_RNG_REPLAY ? 0 : 1;
     const void *kernel = mode == 0 ? (const void *)prepare_fused_kernel<ML2048_RNG_REPLAY> : (const void *)prepare_fused_kernel<ML2048_RNG_PHILOX>;
@@ -1136,6 +1153,7 @@ static int launch_prepare_fused(const ml2048_prepare_args &a, cudaStream_t s)
     const int64_t tiles = (a.num_games + kPrepTile - 1) / kPrepTile;  // the scratch holds one int per tile
     const int64_t blocks = tiles < blocks_here ? tiles : blocks_here;
     if ((n16 + blocks - 1) / blocks > kFusedMaxGroups) return ML2048_E_SIZE;
+    clear_stale_error();
     ml2048_prepare_args args = a;
     int32_t *counts = a.scratch;
     void *params[] = {&args, &counts};
@@ -1149,21 +1167,32 @@ static int launch_prepare_fused(const ml2048_prepare_args &a, cudaStream_t s)
     return e == cudaSuccess ? launch_status() : (int)e;
 }
 
+// ML2048_PREPARE=split in the environment forces the three-launch path (A/B measurements and tests).  The variable is
+// looked up on every call only when ML2048_PREPARE_RECHECK is set when the library first looks (the tests switch modes
+// inside one process); otherwise it is read once.
+static bool force_split_prepare()
+{
+    static const bool recheck = getenv("ML2048_PREPARE_RECHECK") != nullptr;
+    static const bool split_at_start = [] { const char *m = getenv("ML2048_PREPARE"); return m && m[0] == 's'; }();
+    if (!recheck) return split_at_start;
+    const char *m = getenv("ML2048_PREPARE");
+    return m && m[0] == 's';
+}
+
 int ml2048_prepare(const ml2048_prepare_args *args, void *stream)
 {
     int rc = check_prepare_args(args);
     if (rc) return rc;
     if (args->num_games <= kPrepSmallMaxGames && !args->id_offset) {
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        clear_stale_error();
         if (args->rng_mode == ML2048_RNG_REPLAY)
             prepare_small_kernel<ML2048_RNG_REPLAY><<<1, kPrepThreads, 0, s>>>(*args);
         else
             prepare_small_kernel<ML2048_RNG_PHILOX><<<1, kPrepThreads, 0, s>>>(*args);
         return launch_status();
     }
-    // ML2048_PREPARE=split in the environment forces the three-launch path (A/B measurements)
-    const char *mode = getenv("ML2048_PREPARE");
-    if (!args->id_offset && !(mode && mode[0] == 's')) {
+    if (!args->id_offset && !force_split_prepare()) {
         rc = launch_prepare_fused(*args, static_cast<cudaStream_t>(stream));
         if (rc != ML2048_E_SIZE) return rc;  // E_SIZE: the batch does not fit the single-wave kernel, use three launches
     }
@@ -1190,6 +1219,7 @@ int ml2048_reset_state(void *board_a, void *board_b, void *valid_a, void *valid_
         if (e != cudaSuccess) return (int)e;
     }
     const int64_t padded = (num_games + 15) / 16 * 16;
+    clear_stale_error();
     fill_terminated_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, s>>>(terminated, num_games, padded);
     return launch_status();
 }
@@ -1202,6 +1232,7 @@ int ml2048_encode_onehot(const void *board, void *out, int32_t onehot_dtype, int
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const unsigned grid = (unsigned)((num_games + kStepThreads - 1) / kStepThreads);
     const uint4 *b = reinterpret_cast<const uint4 *>(board);
+    clear_stale_error();
     switch (onehot_dtype) {
     case ML2048_ONEHOT_F32: onehot_kernel<ML2048_ONEHOT_F32><<<grid, kStepThreads, 0, s>>>(b, out, num_games); break;
     case ML2048_ONEHOT_BF16: onehot_kernel<ML2048_ONEHOT_BF16><<<grid, kStepThreads, 0, s>>>(b, out, num_games); break;
@@ -1217,6 +1248,7 @@ int ml2048_valid_actions(const void *board, void *valid_out, int64_t num_games, 
     if (!board || !valid_out) return ML2048_E_NULL;
     if (misaligned(board, 16) || misaligned(valid_out, 4)) return ML2048_E_ALIGN;
     const unsigned grid = (unsigned)((num_games + kStepThreads - 1) / kStepThreads);
+    clear_stale_error();
     valid_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4 *>(board),
                                                                                 reinterpret_cast<uint32_t *>(valid_out), num_games);
     return launch_status();
@@ -1229,6 +1261,7 @@ int ml2048_max_tile_hist(const void *board, const uint8_t *terminated, int64_t n
     if (misaligned(board, 16) || misaligned(hist20, 8)) return ML2048_E_ALIGN;
     int64_t grid = (num_games + kStepThreads - 1) / kStepThreads;
     if (grid > 148 * 8) grid = 148 * 8;
+    clear_stale_error();
     max_tile_hist_kernel<<<(unsigned)grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const uint4 *>(board), terminated, num_games, hist20);
     return launch_status();
@@ -1241,6 +1274,7 @@ int ml2048_sample_random_valid(const void *valid, uint8_t *actions_out, int64_t 
     if (!valid || !actions_out) return ML2048_E_NULL;
     if (misaligned(valid, 4)) return ML2048_E_ALIGN;
     const unsigned grid = (unsigned)((num_games + kStepThreads - 1) / kStepThreads);
+    clear_stale_error();
     sample_random_valid_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const uint32_t *>(valid), actions_out, num_games, slot_base, philox_seed, philox_counter);
     return launch_status();
@@ -1253,6 +1287,7 @@ int ml2048_sample_masked_categorical(const float *logits, const void *valid, uin
     if (!logits || !valid || (!actions_u8 && !actions_i64)) return ML2048_E_NULL;
     if (misaligned(logits, 16) || misaligned(valid, 4) || misaligned(actions_i64, 8) || misaligned(log_prob, 4)) return ML2048_E_ALIGN;
     const unsigned grid = (unsigned)((num_games + kStepThreads - 1) / kStepThreads);
+    clear_stale_error();
     sample_categorical_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4 *>(logits), reinterpret_cast<const uint32_t *>(valid), actions_u8,
         reinterpret_cast<long long *>(actions_i64), log_prob, num_games, slot_base, philox_seed, philox_counter);
@@ -1267,6 +1302,7 @@ int ml2048_gae(const float *v0, const float *v1, const float *reward, const uint
     if (misaligned(v0, 4) || misaligned(v1, 4) || misaligned(reward, 4) || misaligned(adv, 4)) return ML2048_E_ALIGN;
     const int64_t total = use_count * game_count;
     const unsigned grid = (unsigned)((total + kStepThreads - 1) / kStepThreads);
+    clear_stale_error();
     gae_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(v0, v1, reward, terminated, adv, step_count, game_count,
                                                                             total, gamma, coef);
     return launch_status();
@@ -1300,6 +1336,56 @@ int ml2048_pack_randperm_keys(const uint8_t *host_randperm, uint8_t *host_keys, 
         if (seen != 0xffffu) return ML2048_E_ENUM;  // not a permutation of 0..15
     }
     return 0;
+}
+
+// host Philox (plain C++ copies of the rounds in board_ops.cuh, which are device functions in this translation unit)
+static void host_philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+    for (int i = 0; i < 10; ++i) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        c[0] = n0, c[1] = (uint32_t)p1, c[2] = n2, c[3] = (uint32_t)p0;
+        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+}
+
+void ml2048_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c[4] = {counter[0], counter[1], counter[2], counter[3]};
+    host_philox4x32_10(c, key[0], key[1]);
+    for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+void ml2048_philox2x32_10(const uint32_t counter[2], uint32_t key, uint32_t out[2])
+{
+    uint32_t c0 = counter[0], c1 = counter[1];
+    for (int i = 0; i < 10; ++i) {
+        const uint64_t p = (uint64_t)0xD256D193u * c0;
+        c0 = (uint32_t)(p >> 32) ^ key ^ c1;
+        c1 = (uint32_t)p;
+        key += 0x9E3779B9u;
+    }
+    out[0] = c0, out[1] = c1;
+}
+
+void ml2048_philox_epoch_draws(uint64_t philox_seed, uint64_t prepare_counter, double two_prob, uint32_t *coin_u32, uint32_t *mask16)
+{
+    // counter words: (prepare counter low, high, stream tag, block index); key = seed
+    const uint32_t k0 = (uint32_t)philox_seed, k1 = (uint32_t)(philox_seed >> 32);
+    uint32_t c[4] = {(uint32_t)prepare_counter, (uint32_t)(prepare_counter >> 32), 0x434F494Eu /* "COIN" */, 0u};
+    host_philox4x32_10(c, k0, k1);
+    if (coin_u32) *coin_u32 = c[0];
+    if (mask16) {
+        const uint32_t thr = ml2048_two_threshold(two_prob);
+        uint32_t m = 0;
+        for (uint32_t b = 0; b < 4; ++b) {
+            uint32_t w[4] = {(uint32_t)prepare_counter, (uint32_t)(prepare_counter >> 32), 0x4D41534Bu /* "MASK" */, b};
+            host_philox4x32_10(w, k0, k1);
+            for (uint32_t j = 0; j < 4; ++j)
+                if (two_prob >= 1.0 || w[j] < thr) m |= 1u << (4 * b + j);
+        }
+        *mask16 = two_prob > 0.0 ? m : 0u;
+    }
 }
 
 uint32_t ml2048_two_threshold(double two_prob)

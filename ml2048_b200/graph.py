@@ -52,6 +52,7 @@ class GraphedRollout:
                     for _ in range(3):  # warm the policy's kernels / workspaces outside the capture
                         logits_fn(env)
                 side.synchronize()
+            env._skip_id_check = True  # the id-range accounting is done per replay() (no device reads while capturing)
             with torch.cuda.graph(self.graph, stream=side):
                 for t in range(self.steps):
                     env.prepare()
@@ -66,6 +67,7 @@ class GraphedRollout:
                     else:
                         env.step(actions, record=record)
                 env._set_record(None)
+            env._skip_id_check = False
         torch.cuda.current_stream(env.device).wait_stream(side)
         # capturing executed nothing on the device: rewind the host mirrors
         env._sched_pos = pos
@@ -78,5 +80,6 @@ class GraphedRollout:
                 if env._sched_pos != env._sched_len:
                     raise RuntimeError("the device schedule was consumed outside this GraphedRollout")
                 env.schedule_ahead(self.window, min_steps=self.window)
+            env._check_id_range(self.steps)  # ids are int32: raise before the device counter could wrap
             self.graph.replay()
             env._sched_pos += self.steps

@@ -33,8 +33,8 @@ def sample_masked_categorical(logits: torch.Tensor, valid: torch.Tensor, *, seed
     """Sample one action per game from softmax(logits restricted to valid) and return (actions, log_probs).
 
     Same distribution and log-probabilities as the reference's ``_sample_action`` (invalid actions masked to
-    finfo.min, ``Categorical(logits=...)``); the uniform comes from Philox4x32-10 keyed by
-    (seed, slot_base + game, counter) instead of ``torch.multinomial``'s generator."""
+    finfo.min, ``Categorical(logits=...)``); the uniform comes from Philox2x32-10 keyed by
+    (seed, slot_base + game, counter) -- the policy word the step kernel itself draws -- instead of ``torch.multinomial``'s generator."""
     _cuda(logits, "logits")
     _cuda(valid, "valid")
     if logits.dtype != torch.float32 or logits.ndim != 2 or logits.shape[1] != 4:

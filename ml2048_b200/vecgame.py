@@ -127,6 +127,44 @@ class _DataView:
     def dtype(self) -> np.dtype:
         return DATA_DTYPE
 
+    # Whole-record lookups are served from a HOST copy of the state arena when that is cheap: the pinned mirror the
+    # NumPy drop-in mode fills at every prepare()/step() of a small batch, or (up to _SNAPSHOT_MAX_GAMES) one copy +
+    # one synchronisation made on the first lookup after the state last changed.  ReplayRecorder.on_prepared reads
+    # ``data[slot]["id"].item()`` in a Python loop over the reset slots (replay.py:147-151): 65 536 lookups at
+    # eval_perf.py's first prepare() cost one 3.5 MB copy instead of 65 536 x nine gathers.  Larger batches gather the
+    # requested records on the device and bring them over with ONE copy.
+    _SNAPSHOT_MAX_GAMES = 1 << 20
+
+    def _host_views(self):
+        env = self._env
+        if env._mirror_epoch == env._state_epoch and env._arena_host is not None:
+            return env._mirror
+        if env._size <= self._SNAPSHOT_MAX_GAMES:
+            return env._mirror_to_host()
+        return None
+
+    @staticmethod
+    def _normalise_key(key: Any, size: int):
+        """-> (index array or None for 'everything', scalar?) without materialising arange(size) for a single slot."""
+        if isinstance(key, (int, np.integer)):
+            k = int(key)
+            if k < -size or k >= size:
+                raise IndexError(f"index {k} is out of bounds for {size} games")
+            return np.asarray([k % size], dtype=np.int64), True
+        if isinstance(key, slice):
+            if key == slice(None):
+                return None, False
+            return np.arange(*key.indices(size), dtype=np.int64), False
+        if isinstance(key, torch.Tensor):
+            key = key.cpu().numpy()
+        key = np.asarray(key)
+        if key.dtype == np.bool_:
+            return np.flatnonzero(key).astype(np.int64), False
+        idx = key.astype(np.int64).reshape(-1)
+        if idx.size and (idx.min() < -size or idx.max() >= size):
+            raise IndexError(f"index out of bounds for {size} games")
+        return np.where(idx < 0, idx + size, idx), False
+
     def __getitem__(self, key: Any):
         env = self._env
         if isinstance(key, str):
@@ -136,20 +174,47 @@ class _DataView:
             if key == "_padding":
                 return np.zeros((env._size, 10), np.uint8)
             return env._fetch(name, force_host=True)
-        scalar = isinstance(key, (int, np.integer))
-        idx = torch.as_tensor(np.atleast_1d(np.arange(env._size)[key]), device=env.device, dtype=torch.long)
-        rec = np.zeros((idx.numel(),), dtype=DATA_DTYPE)
+        idx, scalar = self._normalise_key(key, env._size)
         cur = env._cur
-        rec["id"] = env._id[idx].cpu().numpy()
-        rec["step"] = env._step[idx].cpu().numpy()
-        rec["score"] = env._score[idx].cpu().numpy()
-        rec["reward"] = env._reward[idx].cpu().numpy()
-        rec["board"] = env._board[cur][idx].cpu().numpy()
+        views = self._host_views()
+        if views is not None:
+            take = (lambda a: a.copy()) if idx is None else (lambda a: a[idx])
+            n = env._size if idx is None else idx.size
+            rec = np.zeros((n,), dtype=DATA_DTYPE)
+            rec["id"] = take(views["_id"])
+            rec["step"] = take(views["_step"])
+            rec["score"] = take(views["_score"])
+            rec["reward"] = take(views["_reward"])
+            rec["board"] = take(views["_board"][cur])
+            if env._merged is not None:
+                rec["merged"] = take(views["_merged"])
+            rec["valid_actions"] = take(views["_valid"][cur])
+            rec["terminated"] = take(views["_terminated_padded"][: env._size])
+            rec["invalid"] = take(views["_invalid"])
+            return rec[0] if scalar else rec
+        # large batch: gather the records on the device into one packed buffer, ONE copy to the host
+        if idx is None:
+            idx = np.arange(env._size, dtype=np.int64)
+        didx = torch.from_numpy(idx).to(env.device)
+        n = idx.size
+        packed = torch.zeros((n, DATA_DTYPE.itemsize), dtype=torch.uint8, device=env.device)
+
+        def put(field: str, t: torch.Tensor) -> None:
+            off = DATA_DTYPE.fields[field][1]
+            raw = t.index_select(0, didx).contiguous().view(torch.uint8).reshape(n, -1)
+            packed[:, off:off + raw.shape[1]] = raw
+
+        put("id", env._id)
+        put("step", env._step_score.view(torch.int32)[:, 0])
+        put("score", env._step_score.view(torch.int32)[:, 1])
+        put("reward", env._reward)
+        put("board", env._board[cur])
         if env._merged is not None:
-            rec["merged"] = env._merged[idx].cpu().numpy()
-        rec["valid_actions"] = env._valid[cur][idx].cpu().numpy()
-        rec["terminated"] = env._terminated[idx].cpu().numpy()
-        rec["invalid"] = env._invalid[idx].cpu().numpy()
+            put("merged", env._merged)
+        put("valid_actions", env._valid[cur])
+        put("terminated", env._terminated)
+        put("invalid", env._invalid)
+        rec = packed.cpu().numpy().view(DATA_DTYPE).reshape(n)
         return rec[0] if scalar else rec
 
     def copy(self) -> np.ndarray:
@@ -226,6 +291,8 @@ class VecGame:
             self._arena = torch.zeros((total,), dtype=torch.uint8, device=dev)
             self._arena_layout = offsets
             self._arena_host = None  # pinned mirror, allocated on first use
+            self._state_epoch = 0    # bumped by everything that changes device state; the host mirror remembers its own
+            self._mirror_epoch = -1
             for name, (off, nbytes, dtype, shape) in offsets.items():
                 setattr(self, name, self._arena[off:off + nbytes].view(dtype).view(shape))
             self._terminated = self._terminated_padded[:m]
@@ -274,6 +341,8 @@ class VecGame:
         self._dist_group = None
         self._dist_rank = 0
         self._dist_world = 1
+        self._id_bound = None
+        self._skip_id_check = False
 
         self._step_args = _lib.StepArgs()
         self._prep_args = _lib.PrepareArgs()
@@ -398,6 +467,7 @@ class VecGame:
             self._mirror = views
         self._arena_host.copy_(self._arena, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self._mirror_epoch = self._state_epoch
         return self._mirror
 
     def _mirror_field(self, views: dict[str, np.ndarray], key: str) -> np.ndarray:
@@ -414,8 +484,8 @@ class VecGame:
             return views["_terminated_padded"][: self._size]
         return views["_" + key]
 
-    def _device_field(self, key: str) -> torch.Tensor:
-        cur = self._cur
+    def _device_field(self, key: str, cur: Optional[int] = None) -> torch.Tensor:
+        cur = self._cur if cur is None else cur
         if key == "state":
             return self._board[cur]
         if key == "valid_actions":
@@ -460,7 +530,8 @@ class VecGame:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._tables_pin_events[k] = ev
-        self._two_mask = int(self._lib.ml2048_two_mask(self._randfloat.ctypes.data, self._two_prob))
+        if self._rng_mode == _lib.RNG_REPLAY:  # Philox mode draws its epoch masks from the counter-based stream (_philox_epoch)
+            self._two_mask = int(self._lib.ml2048_two_mask(self._randfloat.ctypes.data, self._two_prob))
 
     _TABLE_BYTES = 2 * RAND_ROWS * 16  # one slot of the table ring
 
@@ -498,15 +569,19 @@ class VecGame:
             ring[slot, 0] = self._randperm
             _lib.check(self._lib.ml2048_pack_randperm_keys(self._randperm.ctypes.data, ring[slot, 1].ctypes.data, RAND_ROWS),
                        "ml2048_pack_randperm_keys")
-            self._two_mask = int(self._lib.ml2048_two_mask(self._randfloat.ctypes.data, self._two_prob))
+            if self._rng_mode == _lib.RNG_REPLAY:
+                self._two_mask = int(self._lib.ml2048_two_mask(self._randfloat.ctypes.data, self._two_prob))
 
         put(0)  # the tables in force now
         slot = 0
         entries = np.zeros((steps, 4), dtype=np.int64)
         n = 0
         while n < steps and self._rng_mode != _lib.RNG_REPLAY:
-            entries[n, 2] = self._philox_counter  # Philox mode: the counter is the whole schedule
+            self._philox_epoch(self._philox_counter)  # Philox mode: the counter and the epoch's 2-vs-4 mask are the schedule
+            entries[n, 2] = self._philox_counter
+            entries[n, 3] = self._two_mask
             self._philox_counter += 2
+            self._rand_step += 1
             n += 1
         while n < steps:
             coin = self._draw_coin()  # game_numba.py:622
@@ -554,6 +629,8 @@ class VecGame:
         self._upload_tables()
         self._philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF if seed is not None else int(np.random.SeedSequence().entropy) & 0xFFFFFFFFFFFFFFFF
         self._philox_counter = 0
+        if self._rng_mode == _lib.RNG_PHILOX:
+            self._philox_epoch(-1)  # the epoch in force after reset(): drawn at counter 2^64 - 1
         with torch.cuda.device(self.device):
             rc = self._lib.ml2048_reset_state(
                 self._p(self._board[0]), self._p(self._board[1]), self._p(self._valid[0]), self._p(self._valid[1]),
@@ -564,8 +641,15 @@ class VecGame:
             self._onehot.zero_()
             self._onehot[:, 0, :] = 1  # an all-empty board encodes as class 0 everywhere
         self._stats_dev.zero_()
+        # the optional device logs restart with the environment: rows from before the reset must not mix with rows after it
+        for name in ("_age", "_traj_state", "_traj_action", "_traj_score", "_traj_rows", "_ep_steps", "_ep_score", "_ep_max_tile"):
+            t = getattr(self, name, None)
+            if t is not None:
+                t.zero_()
         self._cur = 0
         self._obs_cache = None
+        self._state_epoch += 1
+        self._id_bound = None  # upper bound of the id counter, re-read from the device on the next prepare()
 
     def observations(self):
         """game_numba.py:586-587: (board (M,16) u8, valid_actions (M,4) u8)."""
@@ -585,6 +669,8 @@ class VecGame:
         terminated slot in ascending order.  Returns ``(indices,)``."""
         p = self._prep_args
         cur = self._cur
+        self._state_epoch += 1
+        self._check_id_range(1)
         if self._sched_len and self._sched_pos >= self._sched_len:
             self.schedule_ahead(self._sched_len)  # window used up: draw the next one (eager callers only)
         if self._sched_len:
@@ -599,6 +685,8 @@ class VecGame:
                     self._schedule.refresh_tables(self._randperm, self._randfloat)
                     self._upload_tables()
                 rand_offset = self._schedule.offset()
+            else:
+                self._philox_epoch(self._philox_counter)
             p.sched = None
             p.rand_base = self._rand_step + rand_offset
             p.two_mask = self._two_mask
@@ -637,6 +725,39 @@ class VecGame:
         if n == 0:
             return (np.zeros((0,), dtype=np.int64),)
         return (idx.cpu().numpy(),)
+
+    _COIN_REFRESH = int(0.9 * 4294967296.0)  # a 32-bit coin >= this value opens a new table epoch (game_numba.py:622)
+
+    def _philox_epoch(self, counter: int) -> None:
+        """Philox mode, host half of one prepare(): the reference's table-epoch logic (game_numba.py:622-624) with draws
+        from the counter-based stream instead of the numpy generator.  The epoch's 16-bit mask ties the 2-vs-4 choice to
+        the CELL, as the reference's ``randfloat[cell] < two_prob`` does (:207) -- that tie is part of the reference's
+        episode statistics (tests: test_random_policy_episode_statistics_chi2_and_z)."""
+        coin, mask = C.c_uint32(0), C.c_uint32(0)
+        self._lib.ml2048_philox_epoch_draws(self._philox_seed, counter & 0xFFFFFFFFFFFFFFFF, self._two_prob, C.byref(coin), C.byref(mask))
+        if coin.value >= self._COIN_REFRESH or self._rand_step >= self._RAND_SIZE or counter < 0:
+            self._rand_step = 0
+            self._two_mask = mask.value
+
+    _ID_MAX = (1 << 31) - 1  # ids are int32 like the reference's `id` field (game_numba.py:538)
+
+    def _check_id_range(self, prepares: int) -> None:
+        """Game ids are int32 (the reference's record layout).  A prepare() hands out at most one id per game of the
+        (global) batch, so the host keeps an UPPER BOUND of the device-resident id counter and raises before an id
+        could wrap -- at 2^27 games and ~1 % resets per step that is after ~1700 steps.  The bound is refreshed from the
+        device (one synchronisation) only when it comes within reach of 2^31, i.e. practically never for small batches."""
+        if self._skip_id_check:
+            return
+        per_call = self._size * max(1, self._dist_world)
+        bound = self._id_bound
+        if bound is None or bound + prepares * per_call > self._ID_MAX:
+            bound = int(self._game_count_dev.item())  # the true counter
+            if bound + prepares * per_call > self._ID_MAX:
+                # exact check is not possible without knowing how many games will end: refuse while a wrap is possible
+                raise OverflowError(
+                    f"game ids would pass int32: {bound} games started, up to {prepares * per_call} more in this call; "
+                    "set env._game_count = 0 (ids restart) or use smaller shards")
+        self._id_bound = bound + prepares * per_call
 
     def _draw_coin(self) -> float:
         coin = getattr(self, "_pending_coin", None)
@@ -784,6 +905,7 @@ class VecGame:
     @_game_count.setter
     def _game_count(self, value: int) -> None:
         self._game_count_dev.fill_(int(value))
+        self._id_bound = None
 
     @property
     def _prev_state(self):
@@ -813,6 +935,7 @@ class VecGame:
         a = self._step_args
         cur = self._cur
         self._obs_cache = None
+        self._state_epoch += 1
         if self._sched_len:
             if self._sched_pos >= self._sched_len:
                 raise RuntimeError("the device schedule is used up: call prepare() (or schedule_ahead) first")
@@ -868,14 +991,19 @@ class VecGame:
             self._pipe_actions[actions.dtype] = dev_actions
         main = torch.cuda.current_stream(self.device)
         cur = self._cur
+        # this path launches by itself (not through _launch_step): drop what that would have dropped -- the cached
+        # observations of prepare() and the transition-record pointers of an earlier step(record=...), which a
+        # chunked launch must not write through
+        self._obs_cache = None
+        self._set_record(None)
+        self._state_epoch += 1
         # the host draws of this step, once (game_numba.py:670, :681, :685)
         rand_offset = self._schedule.offset() if self._rng_mode == _lib.RNG_REPLAY else 0
         rand_seed = self._rand_step + rand_offset
         self._rand_step += 1
         counter = self._philox_counter
         self._philox_counter += 1
-        self._cur = 1 - cur  # so that _device_field() names the post-step buffers
-        fields = {k: self._device_field(k) for k in fetch}
+        fields = {k: self._device_field(k, 1 - cur) for k in fetch}  # the post-step buffers
         host = {}
         for k, t in fields.items():
             buf = self._host.get(k)
@@ -923,6 +1051,7 @@ class VecGame:
                 with torch.cuda.stream(d2h):
                     for k, t in fields.items():
                         host[k][lo:hi].copy_(t[lo:hi], non_blocking=True)
+        self._cur = 1 - cur  # only now: an exception above leaves the ping-pong state where it was
         d2h.synchronize()
         res = VecStepResult(self)
         for k in fetch:
@@ -959,6 +1088,8 @@ class VecGame:
         restartable and lets a benchmark replay a recorded trajectory."""
         import copy
 
+        if self._sched_len:
+            raise RuntimeError("state_dict() while a device schedule is active is not supported: call schedule_ahead(0) first")
         torch.cuda.current_stream(self.device).synchronize()
         tensors = {
             name: getattr(self, name).clone()
@@ -969,6 +1100,12 @@ class VecGame:
             tensors["_merged"] = self._merged.clone()
         if self._onehot is not None:
             tensors["_onehot"] = self._onehot.clone()
+        # the optional device logs (enable_episode_log / enable_trajectory_log) belong to the state: a restored
+        # environment continues its rows where the snapshot left them
+        for name in ("_age", "_traj_state", "_traj_action", "_traj_score", "_traj_rows", "_ep_steps", "_ep_score", "_ep_max_tile"):
+            t = getattr(self, name, None)
+            if t is not None:
+                tensors[name] = t.clone()
         host = {
             "size": self._size,
             "cur": self._cur,
@@ -982,8 +1119,6 @@ class VecGame:
             "table_slot": self._table_slot,
             "pending_coin": getattr(self, "_pending_coin", None),
         }
-        if self._sched_len:
-            raise RuntimeError("state_dict() while a device schedule is active is not supported: call schedule_ahead(0) first")
         return {"tensors": tensors, "host": host}
 
     def load_state_dict(self, sd: dict[str, Any]) -> None:
@@ -993,9 +1128,11 @@ class VecGame:
         if host["size"] != self._size:
             raise ValueError(f"snapshot holds {host['size']} games, this environment {self._size}")
         for name, t in sd["tensors"].items():
-            dst = getattr(self, name)
+            dst = getattr(self, name, None)
             if dst is None:
                 raise ValueError(f"snapshot has {name} but this environment does not track it")
+            if name != "_tables_dev" and dst.shape != t.shape:
+                raise ValueError(f"snapshot {name} has shape {tuple(t.shape)}, this environment {tuple(dst.shape)}")
             if name == "_tables_dev" and dst.shape != t.shape:
                 self._tables_dev = t.clone()
                 self._table_slots = t.shape[0]
@@ -1013,6 +1150,8 @@ class VecGame:
         self._pending_coin = host.get("pending_coin")
         self._sched_len = self._sched_pos = 0
         self._obs_cache = None
+        self._state_epoch += 1
+        self._id_bound = None
 
     def enable_episode_log(self, capacity: int, id_base: int = 0) -> None:
         """Record (steps, score, max tile) of every finished game whose id lies in [id_base, id_base+capacity),

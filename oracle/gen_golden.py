@@ -17,6 +17,7 @@ What is produced (all from the reference's own functions, reference: src/ml2048/
                        VecStepResult field + ids + reset indices (full or CRC32 digests)
   runner_stack.npz     the reference's VecRunner + RunnerStats + ReplayRecorder driven by a deterministic policy
   gae.npz              compute_gae (gae.py:7-68) on random fp32 inputs with a stand-in critic
+  random_policy_stats.npz  per-seed episode statistics of the reference under the uniform-over-valid policy (16 seeds)
   schedule_*.npz       the host random draws of one rollout recorded from the reference's generator
                        (tables at every refresh, coins, offsets): input of the "replay" mode
 """
@@ -301,12 +302,46 @@ def gen_runner() -> None:
     print(f"runner stack: {len(bufs)} finished recorded games, terminated_count={int(stats.terminated_count)}")
 
 
+def gen_random_stats() -> None:
+    """Episode statistics of the LIVE reference under the uniform-over-valid policy (policy/random.py:24 semantics), one run
+    per seed: M = 8192 games x 1200 steps (the BASELINE.md section 2 protocol, whose seed-2024 figures are reproduced by the
+    first entry).  All games of a run share the spawn tables -- in particular the 2-vs-4 choice is tied to the CELL for a
+    whole table epoch (game_numba.py:207) -- so episodes within a run are not independent draws and the statistics vary
+    between seeds by more than multinomial noise.  The Philox-mode tests measure that over-dispersion from these runs."""
+    from .rollout import pick_actions
+
+    seeds = [2024] + list(range(100, 115))
+    m, steps = 8192, 1200
+    hist = np.zeros((len(seeds), 20), np.int64)
+    episodes = np.zeros(len(seeds), np.int64)
+    step_sum = np.zeros(len(seeds), np.int64)
+    score_sum = np.zeros(len(seeds), np.float64)
+    for i, seed in enumerate(seeds):
+        vg = ref.VecGame(m)
+        vg.reset(seed)
+        rng = np.random.default_rng(seed + 1)
+        for _ in range(steps):
+            vg.prepare()
+            res = vg.step(pick_actions(vg.observations()[1], rng, 0.0))
+            term = res["terminated"] != 0
+            if term.any():
+                np.add.at(hist[i], res["state"][term].max(axis=1), 1)
+                episodes[i] += int(term.sum())
+                step_sum[i] += int(res["step"][term].sum())
+                score_sum[i] += float(res["score"][term].astype(np.float64).sum())
+        print(f"random stats seed {seed}: episodes={episodes[i]} mean steps={step_sum[i]/episodes[i]:.2f} "
+              f"mean score={score_sum[i]/episodes[i]:.1f} hist={hist[i][hist[i] > 0].tolist()}")
+    np.savez_compressed(os.path.join(OUT_DIR, "random_policy_stats.npz"), seeds=np.array(seeds, np.int64),
+                        meta=np.array([m, steps], np.int64), hist=hist, episodes=episodes, step_sum=step_sum, score_sum=score_sum)
+
+
 def main() -> None:
     os.makedirs(OUT_DIR, exist_ok=True)
     print("numba", numba.__version__, "numpy", np.__version__)
     only = set(sys.argv[1:])
     for name, fn in (("kat", gen_kat), ("lines", gen_line_table), ("boards", gen_boards), ("rollouts", gen_rollouts),
-                     ("schedules", gen_schedules), ("gae", gen_gae), ("runner", gen_runner)):
+                     ("schedules", gen_schedules), ("gae", gen_gae), ("runner", gen_runner),
+                     ("random_stats", gen_random_stats)):
         if not only or name in only:
             fn()
     with open(os.path.join(OUT_DIR, "PROVENANCE.txt"), "w") as fh:

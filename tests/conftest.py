@@ -14,6 +14,10 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# the library reads ML2048_PREPARE (fused / split auto-reset) once per process unless this is set before its first
+# prepare(): the split-vs-fused test switches modes inside one process
+os.environ.setdefault("ML2048_PREPARE_RECHECK", "1")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

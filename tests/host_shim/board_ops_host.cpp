@@ -77,6 +77,18 @@ void hs_philox(const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4)
     out4[0] = o.x, out4[1] = o.y, out4[2] = o.z, out4[3] = o.w;
 }
 
+void hs_philox2(const uint32_t *ctr2, uint32_t key, uint32_t *out2)
+{
+    const u32x2 o = philox2x32_10(ctr2[0], ctr2[1], key);
+    out2[0] = o.x, out2[1] = o.y;
+}
+
+void hs_slot_draws(uint64_t slot, uint64_t counter, uint64_t seed, uint32_t tag, uint32_t *out2)
+{
+    const u32x2 o = slot_draws(slot, counter, seed, tag);
+    out2[0] = o.x, out2[1] = o.y;
+}
+
 // batched drivers (keep the Python loops out of the exhaustive tests)
 void hs_move_batch(const uint8_t *boards, int64_t n, int action, uint8_t *out, uint32_t *gain, uint32_t *rank, uint32_t *count,
                    uint8_t *merged, uint32_t *mask_before)

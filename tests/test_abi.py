@@ -94,6 +94,41 @@ def test_two_mask_uses_double_compare(lib):
     assert lib.ml2048_two_threshold(0.5) == 0x80000000
 
 
+def test_host_philox_known_answers_and_epoch_draws(lib):
+    """Host Philox of the library (no GPU): Random123 known answers, and the Philox-mode table-epoch draws."""
+    out4 = np.zeros(4, np.uint32)
+    for ctr, key, want in (((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+                           ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+                           ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+                            (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))):
+        c, k = np.array(ctr, np.uint32), np.array(key, np.uint32)
+        lib.ml2048_philox4x32_10(c.ctypes.data, k.ctypes.data, out4.ctypes.data)
+        assert tuple(int(x) for x in out4) == want
+    out2 = np.zeros(2, np.uint32)
+    for ctr, key, want in (((0, 0), 0, (0xFF1DAE59, 0x6CD10DF2)), ((0xFFFFFFFF,) * 2, 0xFFFFFFFF, (0x2C3F628B, 0xAB4FD7AD)),
+                           ((0x243F6A88, 0x85A308D3), 0x13198A2E, (0xDD7CE038, 0xF62A4C12))):
+        c = np.array(ctr, np.uint32)
+        lib.ml2048_philox2x32_10(c.ctypes.data, key, out2.ctypes.data)
+        assert tuple(int(x) for x in out2) == want
+    coin, mask = ctypes.c_uint32(), ctypes.c_uint32()
+    ones = refresh = 0
+    n = 4000
+    for counter in range(n):
+        lib.ml2048_philox_epoch_draws(99, counter, 0.8, ctypes.byref(coin), ctypes.byref(mask))
+        assert mask.value < (1 << 16)
+        ones += bin(mask.value).count("1")
+        refresh += coin.value >= int(0.9 * 2**32)
+    assert abs(ones / (16 * n) - 0.8) < 0.01 and abs(refresh / n - 0.1) < 0.02
+    lib.ml2048_philox_epoch_draws(99, 7, 0.8, ctypes.byref(coin), ctypes.byref(mask))
+    first = (coin.value, mask.value)
+    lib.ml2048_philox_epoch_draws(99, 7, 0.8, ctypes.byref(coin), ctypes.byref(mask))
+    assert (coin.value, mask.value) == first  # a pure function of (seed, counter): every shard draws the same epoch
+    lib.ml2048_philox_epoch_draws(99, 7, 1.0, ctypes.byref(coin), ctypes.byref(mask))
+    assert mask.value == 0xFFFF
+    lib.ml2048_philox_epoch_draws(99, 7, 0.0, ctypes.byref(coin), ctypes.byref(mask))
+    assert mask.value == 0
+
+
 def test_reward_selection_by_identity():
     import ml2048_b200
     from ml2048_b200.rewards import reward_kind

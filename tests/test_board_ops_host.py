@@ -40,6 +40,8 @@ def shim():
     lib.hs_kth_set_bit16.argtypes = [u32, u32]
     lib.hs_kth_set_bit16.restype = u32
     lib.hs_philox.argtypes = [vp, vp, vp]
+    lib.hs_philox2.argtypes = [vp, u32, vp]
+    lib.hs_slot_draws.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, u32, vp]
     return lib
 
 
@@ -178,6 +180,43 @@ def test_philox_known_answers(shim):
         out = np.zeros(4, np.uint32)
         shim.hs_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data)
         assert tuple(int(x) for x in out) == want
+
+
+PHILOX2X32_KAT = [  # Random123 kat_vectors: philox2x32 10
+    ((0, 0), 0, (0xFF1DAE59, 0x6CD10DF2)),
+    ((0xFFFFFFFF, 0xFFFFFFFF), 0xFFFFFFFF, (0x2C3F628B, 0xAB4FD7AD)),
+    ((0x243F6A88, 0x85A308D3), 0x13198A2E, (0xDD7CE038, 0xF62A4C12)),
+]
+
+
+def test_philox2x32_known_answers(shim):
+    """The block the kernels draw per game-step (board_ops.cuh:philox2x32_10), compiled for the host."""
+    for ctr, key, want in PHILOX2X32_KAT:
+        c = np.array(ctr, np.uint32)
+        out = np.zeros(2, np.uint32)
+        shim.hs_philox2(c.ctypes.data, key, out.ctypes.data)
+        assert tuple(int(x) for x in out) == want
+
+
+def test_slot_draws_key_schedule(shim):
+    """slot_draws = Philox2x32-10 with counter (slot low, counter low) and the seed / high words / stream tag folded into the key."""
+    def ref(slot, counter, seed, tag):
+        m = 0xFFFFFFFF
+        key = (seed & m) ^ (((seed >> 32) * 0x9E3779B9) & m) ^ (((counter >> 32) * 0x85EBCA6B) & m) ^ (((slot >> 32) * 0xC2B2AE35) & m) ^ tag
+        c = np.array([slot & m, counter & m], np.uint32)
+        out = np.zeros(2, np.uint32)
+        shim.hs_philox2(c.ctypes.data, key, out.ctypes.data)
+        return tuple(int(x) for x in out)
+
+    out = np.zeros(2, np.uint32)
+    seen = set()
+    for slot, counter, seed, tag in ((0, 0, 0, 0), (5, 9, 123, 0), (5, 9, 123, 0x80000000), ((1 << 33) + 5, 9, 123, 0),
+                                     (5, (1 << 40) + 9, 123, 0), (5, 9, (7 << 32) + 123, 0), ((1 << 27) - 1, 2**32 - 1, 2**64 - 1, 0)):
+        shim.hs_slot_draws(slot, counter, seed, tag, out.ctypes.data)
+        got = tuple(int(x) for x in out)
+        assert got == ref(slot, counter, seed, tag)
+        seen.add(got)
+    assert len(seen) == 7  # high words and the stream tag all matter
 
 
 def test_hypothesis_boards_against_oracle(shim, oracle):

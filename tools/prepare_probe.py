@@ -1,7 +1,7 @@
 """Timing probe for the auto-reset at steady state: one prepare() per trial from the same snapshot, L2 flushed before.
 
     python tools/prepare_probe.py [--games N] [--onehot f32] [--trials 5]
-ML2048_PREPARE=split|fused (read by the library at every call) picks the three-launch or the single-launch path.
+ML2048_PREPARE=split|fused (read by the library at every call when ML2048_PREPARE_RECHECK is set) picks the three-launch or the single-launch path.
 """
 import argparse
 import os
@@ -18,6 +18,7 @@ p.add_argument("--onehot", default=None)
 p.add_argument("--trials", type=int, default=5)
 p.add_argument("--burn-in", type=int, default=256)
 a = p.parse_args()
+os.environ["ML2048_PREPARE_RECHECK"] = "1"  # the library otherwise reads the switch once per process
 os.environ["ML2048_PREPARE"] = "split"  # the burn-in never runs the path under test
 env = ml2048_b200.VecGame(a.games, output="torch", rng_mode="replay", onehot=a.onehot, track_merged=False, sync_free=True)
 env.reset(0)
