@@ -196,15 +196,49 @@ constexpr int kMoveSelRow = 8;  // words per action
         0x7654u, 0x3210u, 0x7654u, 0x3210u, 0x7654u, 0x3210u, 0u, 0u  /* down  */ \
     }
 
+// The same rows indexed by (valid-direction mask, k): row 4*bits + k holds the selectors of the k-th (0-based) valid direction
+// of the 4-bit mask `bits` and, in word 6, that direction itself.  The in-kernel random policy picks k = floor(u * popc(bits))
+// and fetches the row directly: no search for the k-th set bit (16 ALU instructions before).  Rows 60..63 (bits = 0b1111)
+// are the four directions in order, i.e. the table a caller-given action indexes with 60 + action; k beyond the number of
+// valid directions (only reachable with bits = 0, a finished game idling) maps to direction 0.
+struct PolicySelTable {
+    uint32_t w[64 * kMoveSelRow];
+};
+
+constexpr PolicySelTable make_policy_sel_table()
+{
+    constexpr uint32_t base[4 * kMoveSelRow] = ML2048_MOVE_SEL_TABLE;
+    PolicySelTable t{};
+    for (uint32_t bits = 0; bits < 16; ++bits) {
+        for (uint32_t k = 0; k < 4; ++k) {
+            uint32_t action = 0, seen = 0;
+            bool found = false;
+            for (uint32_t d = 0; d < 4 && !found; ++d) {
+                if ((bits >> d) & 1u) {
+                    if (seen == k) {
+                        action = d;
+                        found = true;
+                    }
+                    ++seen;
+                }
+            }
+            for (int j = 0; j < kMoveSelRow; ++j) t.w[(4 * bits + k) * kMoveSelRow + j] = base[action * kMoveSelRow + j];
+            t.w[(4 * bits + k) * kMoveSelRow + 6] = action;
+        }
+    }
+    return t;
+}
+
 // `sel` = the action's row of the table (16-byte aligned)
-ML2048_FN void move_board_sel(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, const uint32_t *sel, Fusions &f)
+// Returns word 6 of the row (the direction, in the (mask, k)-indexed table).
+ML2048_FN uint32_t move_board_sel(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, const uint32_t *sel, Fusions &f)
 {
 #if defined(__CUDACC__)
     const uint4 sa = __ldg(reinterpret_cast<const uint4 *>(sel));
-    const uint2 sb = __ldg(reinterpret_cast<const uint2 *>(sel + 4));
-    const uint32_t in1a = sa.x, in1b = sa.y, in2a = sa.z, in2b = sa.w, out2a = sb.x, out2b = sb.y;
+    const uint4 sb = __ldg(reinterpret_cast<const uint4 *>(sel + 4));
+    const uint32_t in1a = sa.x, in1b = sa.y, in2a = sa.z, in2b = sa.w, out2a = sb.x, out2b = sb.y, row_action = sb.z;
 #else
-    const uint32_t in1a = sel[0], in1b = sel[1], in2a = sel[2], in2b = sel[3], out2a = sel[4], out2b = sel[5];
+    const uint32_t in1a = sel[0], in1b = sel[1], in2a = sel[2], in2b = sel[3], out2a = sel[4], out2b = sel[5], row_action = sel[6];
 #endif
     // prmt_sign = the raw PRMT (no selector nibble of the table has its sign-replication bit set); __byte_perm would
     // first mask a selector it cannot see to 0x7777
@@ -216,6 +250,7 @@ ML2048_FN void move_board_sel(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t
     r1 = prmt_sign(u0, u1, out2b);
     r2 = prmt_sign(u2, u3, out2a);
     r3 = prmt_sign(u2, u3, out2b);
+    return row_action;
 }
 
 #if !defined(__CUDACC__)

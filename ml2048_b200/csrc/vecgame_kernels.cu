@@ -211,6 +211,8 @@ __device__ __forceinline__ void write_onehot_warp_dyn(int dtype, uint4 board, vo
 // direction -> permute selectors of the move (board_ops.cuh): 128 bytes that live in L1; a game's row is fetched with two
 // read-only vector loads (no shared-memory copy, so no barrier at the start of the block)
 __device__ const uint32_t d_move_sel[4 * kMoveSelRow] = ML2048_MOVE_SEL_TABLE;
+// ... and the same rows indexed by (valid-direction mask, k) for the in-kernel random policy (2 KiB, L1-resident)
+__device__ const PolicySelTable d_policy_sel = make_policy_sel_table();
 
 __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, int64_t g)
 {
@@ -274,12 +276,13 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
 #endif
             return reinterpret_cast<const uint32_t *>(a.valid_in)[g];
         };
+        const uint32_t *sel_row;  // the move's permute selectors (board_ops.cuh)
         if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
-            // uniform over the valid directions (policy/random.py:17-27); 0 when the game is over
+            // uniform over the valid directions (policy/random.py:17-27), direction 0 when the game is over: k = floor(u * nvalid)
+            // indexes the (mask, k) table, whose row carries the selectors AND the direction -- no search for the k-th set bit
             const uint32_t bits = mask_bits4(current_mask());
-            const uint32_t nv = popc32(bits);
-            action = nv ? kth_valid_action(bits, umulhi32(rnd.y, nv)) : 0u;
-            if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
+            sel_row = d_policy_sel.w + (bits * 4u + umulhi32(rnd.y, popc32(bits))) * kMoveSelRow;
+            action = 0u;  // read from the row below
         } else if (kFull && a.action_mode == ML2048_ACTIONS_FROM_LOGITS) {
             const uint32_t bits = mask_bits4(current_mask());
             const float4 lg = reinterpret_cast<const float4 *>(a.logits)[g];
@@ -287,8 +290,10 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
             action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.y, lp);
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
             if (a.log_prob_out) a.log_prob_out[g] = lp;
+            sel_row = d_move_sel + (action & 3u) * kMoveSelRow;
         } else {
             action = load_action(a.actions, a.action_dtype, g);
+            sel_row = d_move_sel + (action & 3u) * kMoveSelRow;
         }
 
         uint32_t r0 = bd.x, r1 = bd.y, r2 = bd.z, r3 = bd.w;
@@ -296,7 +301,11 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
         float tr_reward = 0.0f, tr_score = 0.0f;
         int32_t tr_step = 0;
         uint32_t tr_term = 0u, tr_mask = 0u;
-        move_board_sel(r0, r1, r2, r3, d_move_sel + (action & 3u) * kMoveSelRow, f);
+        const uint32_t row_action = move_board_sel(r0, r1, r2, r3, sel_row, f);
+        if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
+            action = row_action;
+            if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
+        }
         // valid_actions[action] (game_numba.py:718) == "the move changes the board"; out-of-range
         // actions (which the reference would index out of bounds with) count as invalid moves
         const bool moved = (action < 4u) && (((r0 ^ bd.x) | (r1 ^ bd.y) | (r2 ^ bd.z) | (r3 ^ bd.w)) != 0u);

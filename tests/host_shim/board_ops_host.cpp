@@ -77,6 +77,19 @@ void hs_philox(const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4)
     out4[0] = o.x, out4[1] = o.y, out4[2] = o.z, out4[3] = o.w;
 }
 
+// the (mask, k)-indexed selector table of the in-kernel random policy: copies the 64 rows of 8 words
+void hs_policy_sel_table(uint32_t *out512)
+{
+    static const PolicySelTable t = make_policy_sel_table();
+    memcpy(out512, t.w, sizeof(t.w));
+}
+
+void hs_move_sel_table(uint32_t *out32)
+{
+    static const uint32_t base[4 * kMoveSelRow] = ML2048_MOVE_SEL_TABLE;
+    memcpy(out32, base, sizeof(base));
+}
+
 void hs_philox2(const uint32_t *ctr2, uint32_t key, uint32_t *out2)
 {
     const u32x2 o = philox2x32_10(ctr2[0], ctr2[1], key);

@@ -182,6 +182,27 @@ def test_philox_known_answers(shim):
         assert tuple(int(x) for x in out) == want
 
 
+def test_policy_selector_table(shim):
+    """Row 4*bits + k of the random policy's table = the selector row of the k-th valid direction of `bits`, which it also
+    names in word 6; rows 60..63 are the four directions in order."""
+    shim.hs_policy_sel_table.argtypes = [ctypes.c_void_p]
+    shim.hs_move_sel_table.argtypes = [ctypes.c_void_p]
+    tab = np.zeros((64, 8), np.uint32)
+    base = np.zeros((4, 8), np.uint32)
+    shim.hs_policy_sel_table(tab.ctypes.data)
+    shim.hs_move_sel_table(base.ctypes.data)
+    for bits in range(16):
+        valid = [d for d in range(4) if bits >> d & 1]
+        for k in range(4):
+            action = valid[k] if k < len(valid) else 0
+            if k < len(valid):
+                assert shim.hs_kth_valid_action(bits, k) == action
+            row = tab[4 * bits + k]
+            assert row[6] == action and row[7] == 0
+            np.testing.assert_array_equal(row[:6], base[action][:6])
+    assert [int(tab[60 + a][6]) for a in range(4)] == [0, 1, 2, 3]
+
+
 PHILOX2X32_KAT = [  # Random123 kat_vectors: philox2x32 10
     ((0, 0), 0, (0xFF1DAE59, 0x6CD10DF2)),
     ((0xFFFFFFFF, 0xFFFFFFFF), 0xFFFFFFFF, (0x2C3F628B, 0xAB4FD7AD)),

@@ -96,6 +96,7 @@ def test_kernels_stay_inside_their_buffers(m, onehot):
     for t in range(40):
         counter = ref._philox_counter
         ref.prepare()
+        p.two_mask = a.two_mask = ref._two_mask  # Philox mode: the table epoch's 2-vs-4 mask, drawn on the host per prepare()
         p.board, p.valid, p.philox_counter = board[cur].data_ptr(), valid[cur].data_ptr(), counter
         assert lib.ml2048_prepare(C.byref(p), stream) == 0
         a.board_in, a.board_out = board[cur].data_ptr(), board[1 - cur].data_ptr()
