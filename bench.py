@@ -55,6 +55,8 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (core-only, small M)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-fused-reset", action="store_true",
+                   help="timed region: prepare() and step_random() as two calls instead of step_random(auto_reset=True)")
     p.add_argument("--cpu-games", type=int, default=0,
                    help="games per CPU step of the reference arm (0 = the GPU arm's games per GPU, halved until the run fits --ref-budget-s)")
     p.add_argument("--ref-budget-s", type=float, default=420.0, help="wall-clock budget of the --impl reference run")
@@ -578,13 +580,18 @@ def run_b200_arm(args: argparse.Namespace) -> None:
         else:
             pending.append((None, None, sums, mx))
 
+    fused = not args.no_fused_reset
+
     def run_steps(e, n: int, kernel_events=None) -> int:
         reduces = 0
         for i in range(n):
-            e.prepare()
+            if not fused:
+                e.prepare()
             if kernel_events is not None:
                 kernel_events[i][0].record()
-            e.step_random()
+            # fused: the auto-reset rides inside the step kernel (same arrays afterwards as prepare() + step_random(),
+            # tests/test_fused_autoreset.py); a one-block-per-32k-games scan of the terminated flags ranks the resets first
+            e.step_random(auto_reset=fused)
             if kernel_events is not None:
                 kernel_events[i][1].record()
             if kernel_events is not None and (i + 1) % stats_every == 0:
@@ -647,7 +654,8 @@ def run_b200_arm(args: argparse.Namespace) -> None:
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
-        "kernel": "step_kernel<replay, onehot f32> (move+reward+spawn+mask+terminal+one-hot)",
+        "kernel": "step_kernel<replay, onehot f32> (move+reward+spawn+mask+terminal+one-hot" + (
+            "+auto-reset; kernel_ms includes the ~3 us scan of the terminated flags that precedes it)" if fused else ")"),
         "achieved": achieved,
         "peak": peak,
         "peak_source": peak_src,
@@ -783,8 +791,9 @@ def run_b200_arm(args: argparse.Namespace) -> None:
             "host_affinity": numa,
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": (4 if split else 2) * k_steps,
-            "launches_per_step": ("prepare_count, prepare_scan, prepare_apply, step_kernel" if split
+            "gpu_launches": (2 if fused else 4 if split else 2) * k_steps,
+            "launches_per_step": ("autoreset_scan_kernel, step_kernel with the auto-reset fused in" if fused
+                                  else "prepare_count, prepare_scan, prepare_apply, step_kernel" if split
                                   else "prepare_fused_kernel (one cooperative launch), step_kernel"),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
@@ -812,36 +821,41 @@ def measure_extras(ml2048_b200, torch, dev, seed: int) -> dict:
     training shapes of run_train3.py (BASELINE configs[1]) replayed as a 16-step CUDA graph."""
     out = {}
 
-    def timed(env, n, graph_steps=0):
+    def timed(env, n, graph_steps=0, fused=False):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if graph_steps:
-            roll = ml2048_b200.GraphedRollout(env, graph_steps, window=graph_steps * 16)
+            roll = ml2048_b200.GraphedRollout(env, graph_steps, window=graph_steps * 16, auto_reset=fused)
             roll.replay(1)
             torch.cuda.synchronize()
             a.record()
             roll.replay(n // graph_steps)
             b.record()
         else:
+            def one():
+                if not fused:
+                    env.prepare()
+                env.step_random(auto_reset=fused)
+
             for _ in range(5):
-                env.prepare()
-                env.step_random()
+                one()
             torch.cuda.synchronize()
             a.record()
             for _ in range(n):
-                env.prepare()
-                env.step_random()
+                one()
             b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n
 
-    for name, kw, m, n, graph_steps in (
-        ("core_only_replay_M2^24", dict(rng_mode="replay"), 1 << 24, 48, 0),
-        ("core_only_philox_M2^24", dict(rng_mode="philox"), 1 << 24, 48, 0),
-        ("fused_bf16_onehot_M2^24", dict(rng_mode="replay", onehot="bf16"), 1 << 24, 48, 0),
-        ("fused_u8_onehot_M2^24", dict(rng_mode="replay", onehot="u8"), 1 << 24, 48, 0),
-        ("train_shape_M2048_fused_f32_eager", dict(rng_mode="replay", onehot="f32"), 2048, 192, 0),
-        ("train_shape_M2048_fused_f32_graph16", dict(rng_mode="replay", onehot="f32"), 2048, 192, 16),
-        ("train_shape_M4096_fused_f32_graph16", dict(rng_mode="replay", onehot="f32"), 4096, 192, 16),
+    for name, kw, m, n, graph_steps, fused in (
+        ("core_only_replay_M2^24", dict(rng_mode="replay"), 1 << 24, 48, 0, True),
+        ("core_only_replay_M2^24_separate_prepare", dict(rng_mode="replay"), 1 << 24, 48, 0, False),
+        ("core_only_philox_M2^24", dict(rng_mode="philox"), 1 << 24, 48, 0, True),
+        ("fused_bf16_onehot_M2^24", dict(rng_mode="replay", onehot="bf16"), 1 << 24, 48, 0, True),
+        ("fused_u8_onehot_M2^24", dict(rng_mode="replay", onehot="u8"), 1 << 24, 48, 0, True),
+        ("train_shape_M2048_fused_f32_eager", dict(rng_mode="replay", onehot="f32"), 2048, 192, 0, False),
+        ("train_shape_M2048_fused_f32_graph16", dict(rng_mode="replay", onehot="f32"), 2048, 192, 16, False),
+        ("train_shape_M2048_fused_f32_graph16_fused_reset", dict(rng_mode="replay", onehot="f32"), 2048, 192, 16, True),
+        ("train_shape_M4096_fused_f32_graph16", dict(rng_mode="replay", onehot="f32"), 4096, 192, 16, False),
     ):
         env = ml2048_b200.VecGame(m, ml2048_b200.reward_fn_improved if m < 100000 else None, output="torch",
                                   track_merged=False, sync_free=True, device=dev, **kw)
@@ -849,9 +863,12 @@ def measure_extras(ml2048_b200, torch, dev, seed: int) -> dict:
         for _ in range(64 if m > 100000 else 128):
             env.prepare()
             env.step_random()
-        ms = timed(env, n, graph_steps)
-        out[name] = {"us_per_step": ms * 1e3, "env_steps_per_s": m / (ms * 1e-3)}
-        if name == "core_only_replay_M2^24":
+        ms = timed(env, n, graph_steps, fused)
+        out[name] = {"us_per_step": ms * 1e3, "env_steps_per_s": m / (ms * 1e-3), "auto_reset": "fused into the step kernel" if fused
+                     else "separate prepare() launch"}
+        if m >= 1 << 24:
+            out[name]["hbm_frac_whole_step_core_bytes"] = BYTES_CORE * m / (ms * 1e-3) / 1e9 / load_peaks()[0] if "onehot" not in kw else None
+        if name == "core_only_replay_M2^24_separate_prepare":
             # the environment alone: actions GIVEN (recorded from this trajectory, device-resident), step kernel timed by itself
             snap = env.state_dict()
             k = 24

@@ -154,7 +154,7 @@ typedef struct {
      * episode_id_base + episode_capacity) finishes, its final step count, score and max tile exponent are stored
      * at index id - episode_id_base.  This is what eval_perf.py gathers through ReplayRecorder for the games
      * with `buffer.id < rounds` (eval_perf.py:80-102, replay.py:110-232) without any per-step host loop. */
-    const int32_t *id;             /* [num_games] game ids (the array ml2048_prepare maintains) */
+    int32_t *id;                   /* [num_games] game ids (the array ml2048_prepare maintains; written by the fused auto-reset) */
     int64_t episode_id_base;
     int64_t episode_capacity;
     int32_t *episode_steps;        /* [episode_capacity] */
@@ -189,6 +189,22 @@ typedef struct {
     int8_t *traj_action;           /* [traj_capacity][traj_max_rows] */
     float *traj_score;             /* [traj_capacity][traj_max_rows] */
     int32_t *traj_rows;            /* [traj_capacity]: rows written (= steps + 1 once the game is over) */
+
+    /* Fused auto-reset (ML2048_ACTIONS_RANDOM_VALID only; null = off): the games that are over when the step starts are
+     * first reset exactly as ml2048_prepare resets them -- record cleared, id = *reset_id_base + rank of the slot among
+     * the finished slots (slot-ordered, game_numba.py:641-644), two tiles spawned with the PREPARE draws below, the
+     * ascending index list -- and then played, in ONE launch.  board_in / valid_in receive the post-reset board and mask
+     * of those games, so every array equals what ml2048_prepare followed by ml2048_step leaves behind.
+     * reset_rank / reset_chunk_base / reset_id_base come from ml2048_autoreset_scan (run on the same stream right before);
+     * `id` must be writable then.  A game counts as over when its mask is all zero, which is what `terminated` records
+     * (game_numba.py:734-735): the two must agree, as they do for every state the library itself produces. */
+    const int32_t *reset_rank;       /* [ceil(num_games / 32)]: finished games in lower groups of the same 1024-group chunk */
+    const int32_t *reset_chunk_base; /* [ceil(groups / 1024)]: finished games in lower chunks */
+    const int64_t *reset_id_base;    /* device scalar: id of the first game this step resets */
+    int64_t *reset_indices;          /* [num_games] out or null: ascending slots reset by this step (np.flatnonzero, :629) */
+    const uint8_t *randperm;         /* replay mode: the permutation table itself (reset takes the first two entries, :648-655) */
+    int64_t rand_base;               /* prepare's _rand_step + rand_offset (:651); sched entries carry their own */
+    uint64_t prepare_philox_counter; /* Philox mode: the counter ml2048_prepare would have used */
 } ml2048_step_args;
 
 /* Arguments of the auto-reset.  Replaces the host loop of VecGame.prepare (game_numba.py:629-658):
@@ -286,6 +302,17 @@ ML2048_API int ml2048_sample_masked_categorical(const float *logits, const void 
  * rounded exactly like the reference's torch fp32 ops (no fused multiply-add). */
 ML2048_API int ml2048_gae(const float *v0, const float *v1, const float *reward, const uint8_t *terminated, float *adv,
                           int64_t use_count, int64_t step_count, int64_t game_count, float gamma, float coef, void *stream);
+
+/* ---- fused auto-reset: the scan that ranks the finished games -----------------------------------------------------
+ * One launch over the `terminated` flags ([ceil16(num_games)], padded like ml2048_prepare's): per group of 32 slots the
+ * number of finished games, reset_rank[w] = exclusive prefix of those counts inside the group's chunk of 1024 groups,
+ * reset_chunk_base[c] = exclusive prefix over chunks, *reset_id_base = *game_count (+ *id_offset), *game_count += total
+ * (unless id_offset is set: sharded ids, the caller adds the global total), *reset_count = total.
+ * scratch: [ml2048_autoreset_scratch_ints(num_games)] int32, zero before the first call. */
+ML2048_API int ml2048_autoreset_scan(const uint8_t *terminated, int32_t *reset_rank, int32_t *reset_chunk_base, int64_t num_games,
+                                     int64_t *game_count, const int64_t *id_offset, int64_t *reset_id_base, int64_t *reset_count,
+                                     int32_t *scratch, void *stream);
+ML2048_API int64_t ml2048_autoreset_scratch_ints(int64_t num_games);
 
 /* host helpers (no GPU work) */
 ML2048_API uint32_t ml2048_two_mask(const float *host_randfloat16, double two_prob);   /* game_numba.py:207 (f32 -> f64 compare) */

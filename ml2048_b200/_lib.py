@@ -10,7 +10,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libml2048_b200.so")
+# ML2048_LIB selects another build of the SAME sources (A/B experiments with -D switches, tools/variants.sh); it must export
+# the full ABI like the default library
+LIB_PATH = os.environ.get("ML2048_LIB") or os.path.join(_HERE, "libml2048_b200.so")
 
 ABI_VERSION = 9
 STATS_REPLICAS = 64
@@ -85,6 +87,13 @@ class StepArgs(C.Structure):
         ("traj_action", C.c_void_p),
         ("traj_score", C.c_void_p),
         ("traj_rows", C.c_void_p),
+        ("reset_rank", C.c_void_p),
+        ("reset_chunk_base", C.c_void_p),
+        ("reset_id_base", C.c_void_p),
+        ("reset_indices", C.c_void_p),
+        ("randperm", C.c_void_p),
+        ("rand_base", C.c_int64),
+        ("prepare_philox_counter", C.c_uint64),
     ]
 
 
@@ -148,6 +157,8 @@ SYMBOLS = {
     "ml2048_prepare": (C.c_int, [C.POINTER(PrepareArgs), _VP]),
     "ml2048_prepare_count": (C.c_int, [C.POINTER(PrepareArgs), _VP]),
     "ml2048_prepare_apply": (C.c_int, [C.POINTER(PrepareArgs), _VP]),
+    "ml2048_autoreset_scratch_ints": (_I64, [_I64]),
+    "ml2048_autoreset_scan": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ml2048_reset_state": (C.c_int, [_VP] * 11 + [_I64, _VP]),
     "ml2048_encode_onehot": (C.c_int, [_VP, _VP, _I32, _I64, _VP]),
     "ml2048_valid_actions": (C.c_int, [_VP, _VP, _I64, _VP]),

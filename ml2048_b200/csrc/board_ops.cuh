@@ -407,6 +407,48 @@ ML2048_FN u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
     return u32x4{c0, c1, c2, c3};
 }
 
+// Every board a reset can produce: two tiles on an empty board (game_numba.py:648-655).  Entry
+//   idx = (c0 << 6) | (c1 << 2) | (t0 << 1) | t1      c = cell of the first / second tile, t = 1 for a 2-tile, 0 for a 4-tile
+// holds the board (four row words) and its valid-action word, so the auto-reset looks both up with two loads instead of
+// building the board with 64-bit shifts and running the 75-instruction mask on it -- the fused auto-reset executes this
+// once per WARP that holds a finished game (a quarter of all warps in steady state), so its length matters.
+struct FreshTable {
+    uint32_t board[1024 * 4];
+    uint32_t mask[1024];
+};
+
+constexpr uint32_t scalar_valid_word(const uint8_t (&b)[16])
+{
+    bool l = false, r = false, u = false, d = false;
+    for (int row = 0; row < 4; ++row) {
+        for (int col = 0; col < 4; ++col) {
+            const uint8_t x = b[4 * row + col];
+            if (x == 0) continue;
+            if (col > 0 && (b[4 * row + col - 1] == 0 || b[4 * row + col - 1] == x)) l = true;
+            if (col < 3 && (b[4 * row + col + 1] == 0 || b[4 * row + col + 1] == x)) r = true;
+            if (row > 0 && (b[4 * (row - 1) + col] == 0 || b[4 * (row - 1) + col] == x)) u = true;
+            if (row < 3 && (b[4 * (row + 1) + col] == 0 || b[4 * (row + 1) + col] == x)) d = true;
+        }
+    }
+    return (l ? 1u : 0u) | (r ? 0x100u : 0u) | (u ? 0x10000u : 0u) | (d ? 0x1000000u : 0u);
+}
+
+constexpr FreshTable make_fresh_table()
+{
+    FreshTable t{};
+    for (uint32_t idx = 0; idx < 1024; ++idx) {
+        const uint32_t c0 = idx >> 6, c1 = (idx >> 2) & 15u, t0 = (idx >> 1) & 1u, t1 = idx & 1u;
+        uint8_t b[16] = {};
+        b[c0] = (uint8_t)(2u - t0);
+        b[c1] = (uint8_t)(b[c1] | (2u - t1));  // c0 == c1 cannot occur (distinct cells); OR like the kernel's put_cell
+        for (int row = 0; row < 4; ++row)
+            t.board[4 * idx + row] = (uint32_t)b[4 * row] | ((uint32_t)b[4 * row + 1] << 8) | ((uint32_t)b[4 * row + 2] << 16) |
+                                     ((uint32_t)b[4 * row + 3] << 24);
+        t.mask[idx] = scalar_valid_word(b);
+    }
+    return t;
+}
+
 // Philox2x32-10 (same family, Random123): two 32-bit words per block, half the multiplies and xors of Philox4x32-10.
 // A game-step consumes two uniform words -- the spawn cell (Philox mode) and the policy's action -- so this is the block
 // the kernels draw; the 4x32 variant serves the host-side epoch draws (ml2048_philox_epoch_draws).

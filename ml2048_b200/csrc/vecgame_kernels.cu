@@ -206,6 +206,53 @@ __device__ __forceinline__ void write_onehot_warp_dyn(int dtype, uint4 board, vo
     else if (dtype == ML2048_ONEHOT_U8) write_onehot_warp<ML2048_ONEHOT_U8>(board, out_base, game, lane);
 }
 
+// The random inputs of one prepare(): scalar arguments, or the pre-drawn schedule entry a CUDA graph replays.
+struct PrepDraws {
+    int64_t rand_base;
+    uint32_t two_mask;
+    uint64_t philox_counter;
+    const uint8_t *perm_table;
+};
+
+__device__ __forceinline__ PrepDraws load_prep_draws(const ml2048_prepare_args &a)
+{
+    PrepDraws d{a.rand_base, a.two_mask, a.philox_counter, a.randperm};
+    if (a.sched) {
+        const ml2048_sched_entry e = a.sched[*a.sched_cursor];
+        d.rand_base = e.rand_base;
+        d.two_mask = e.two_mask;
+        d.philox_counter = e.philox_counter;
+        d.perm_table += (int64_t)e.table * a.table_stride;
+    }
+    return d;
+}
+
+// all 1024 boards a reset can produce and their valid-action words (board_ops.cuh): 20 KiB, L1/L2-resident
+__device__ const FreshTable d_fresh = make_fresh_table();
+
+// The two tiles a reset spawns on the empty board (game_numba.py:648-655 with :207): replay mode takes the first two
+// entries of the slot's table row, Philox mode two distinct uniform cells; 2 or 4 by the table epoch's per-cell mask.
+// Returns the board and (in `mask`) its valid-action word, both looked up.
+template <int kRng>
+__device__ __forceinline__ uint4 fresh_board(const PrepDraws &d, uint64_t slot, uint64_t philox_seed, uint32_t &mask)
+{
+    uint32_t c0, c1;
+    if (kRng == ML2048_RNG_REPLAY) {
+        const uint32_t row = ((uint32_t)d.rand_base + (uint32_t)slot) & (uint32_t)(kRandRows - 1);  // (rand_base + slot) mod 1024, both >= 0
+        const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(d.perm_table) + row * 4);
+        c0 = p & 15u;
+        c1 = (p >> 8) & 15u;
+    } else {
+        const u32x2 rnd = slot_draws(slot, d.philox_counter, philox_seed, kResetStream);
+        c0 = rnd.x >> 28;
+        c1 = umulhi32(rnd.y, 15u);
+        c1 += (c1 >= c0) ? 1u : 0u;
+    }
+    const uint32_t idx = (c0 << 6) | (c1 << 2) | (((d.two_mask >> c0) & 1u) << 1) | ((d.two_mask >> c1) & 1u);
+    mask = __ldg(d_fresh.mask + idx);
+    return __ldg(reinterpret_cast<const uint4 *>(d_fresh.board) + idx);
+}
+
 // ---- the step kernel ------------------------------------------------------------------------
 
 // direction -> permute selectors of the move (board_ops.cuh): 128 bytes that live in L1; a game's row is fetched with two
@@ -227,12 +274,15 @@ __device__ __forceinline__ uint32_t load_action(const void *actions, int dtype, 
 // Replaces _vec_step (game_numba.py:701-738) + the prev copies of VecGame.step (:672-673).
 // kFull adds the rollout extras (policy-logits sampling, transition record, episode log); the lean variant
 // compiles them out so the plain step pays nothing for them.
-template <int kRng, bool kLog, int kOneHot, bool kFull, int kThreads>
+// kReset fuses the auto-reset (ml2048_prepare) into the step: see ml2048_step_args::reset_rank.
+template <int kRng, bool kLog, int kOneHot, bool kFull, int kThreads, bool kReset = false>
 // lean variants in small blocks: all 2048 thread slots of an SM filled, i.e. <= 32 registers; the variants with the rollout
 // extras hold more live values and are left to the register allocator (no spills)
-__global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOneHotStepMinBlocks
-                                            : kFull                         ? 1
-                                                                            : (2048 / kThreads > 32 ? 32 : 2048 / kThreads))
+// (the fused-reset variants WITH a one-hot are HBM-bound and carry a few more live values: 1536 threads per SM, 42 registers)
+__global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads              ? kOneHotStepMinBlocks
+                                            : kFull                                     ? 1
+                                            : (kReset && kOneHot != ML2048_ONEHOT_NONE) ? (1536 / kThreads > 32 ? 32 : 1536 / kThreads)
+                                                                                        : (2048 / kThreads > 32 ? 32 : 2048 / kThreads))
     step_kernel(const ml2048_step_args a)
 {
     __shared__ uint4 sboards[kOneHot != ML2048_ONEHOT_NONE ? kThreads : 1];
@@ -259,23 +309,61 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
         if (a.sched_cursor_next && blockIdx.x == 0 && threadIdx.x == 0) *a.sched_cursor_next = cursor + 1;
     }
 
+    // fused auto-reset: which lanes of this warp hold a finished game (all non-exited lanes vote; a finished game is one
+    // whose mask is all zero, game_numba.py:734-735)
+    uint4 bd = make_uint4(0, 0, 0, 0);
+    uint32_t mask_now = 0u;   // the CURRENT valid-action word, when the variant needs it before the move
+    const bool want_mask = kReset || a.action_mode != ML2048_ACTIONS_GIVEN;
     if (live) {
-        const uint4 bd = reinterpret_cast<const uint4 *>(a.board_in)[g];
+        bd = reinterpret_cast<const uint4 *>(a.board_in)[g];
+        // The current mask is a function of the current board.  The variants with a fused one-hot are HBM-bound with
+        // idle issue slots, and every extra READ stream costs a write-dominated kernel far more than its bytes (DRAM bus
+        // turnarounds: tools/write_patterns.cu), so they recompute the mask (~45 instructions) instead of loading it; the
+        // issue-bound core-only kernel loads it.
+        if (want_mask) {
+#if !defined(ML2048_LOAD_MASK)
+            if (kOneHot != ML2048_ONEHOT_NONE) mask_now = valid_mask(bd.x, bd.y, bd.z, bd.w);
+            else
+#endif
+                mask_now = reinterpret_cast<const uint32_t *>(a.valid_in)[g];
+        }
+    }
+    bool was_reset = false;
+    if (kReset) {
+        const bool over = live && mask_now == 0u;
+        const uint32_t over_lanes = __ballot_sync(0xffffffffu, over);
+        if (over) {
+            // rank of this slot among all finished slots (slot order): lower chunks + lower groups of the chunk + lower lanes
+            // (a shard holds fewer than 2^31 games: 32-bit indices)
+            const uint32_t group = (uint32_t)g >> 5;
+            const int32_t order = __ldg(a.reset_chunk_base + (group >> 10)) + __ldg(a.reset_rank + group) +
+                                  __popc(over_lanes & ((1u << (threadIdx.x & 31)) - 1u));
+            // the PREPARE draws of this runner step (scalar arguments, or the pre-drawn schedule entry)
+            PrepDraws d{a.rand_base, two_mask, a.prepare_philox_counter, a.randperm};
+            if (a.sched) {
+                const ml2048_sched_entry e = a.sched[*a.sched_cursor];
+                d.rand_base = e.rand_base;
+                d.philox_counter = e.philox_counter;
+                d.perm_table += (int64_t)e.table * a.table_stride;
+            }
+            bd = fresh_board<kRng>(d, (uint64_t)(a.slot_base + g), a.philox_seed, mask_now);
+            // prev_state / prev_valid_actions of this step are the post-reset board and mask (game_numba.py:672-673)
+            reinterpret_cast<uint4 *>(const_cast<void *>(a.board_in))[g] = bd;
+            reinterpret_cast<uint32_t *>(const_cast<void *>(a.valid_in))[g] = mask_now;
+            a.id[g] = (int32_t)*a.reset_id_base + order;
+            if (a.reset_indices && (int64_t)order < a.num_games) a.reset_indices[order] = g;
+            if (a.age) a.age[g] = 0;
+            was_reset = true;
+        }
+    }
+
+    if (live) {
         const uint64_t slot = (uint64_t)(a.slot_base + g);
         // one Philox2x32-10 block per game-step: .x picks the spawn cell (Philox mode), .y is the policy's uniform word
         u32x2 rnd = {0u, 0u};
         if (kRng == ML2048_RNG_PHILOX || a.action_mode != ML2048_ACTIONS_GIVEN) rnd = slot_draws(slot, philox_counter, a.philox_seed, 0u);
         uint32_t action;
-        // The current mask is a function of the current board.  The variants with a fused one-hot are HBM-bound with
-        // idle issue slots, and every extra READ stream costs a write-dominated kernel far more than its bytes (DRAM bus
-        // turnarounds: tools/write_patterns.cu), so they recompute the mask (~45 instructions) instead of loading it; the
-        // issue-bound core-only kernel loads it.
-        const auto current_mask = [&]() -> uint32_t {
-#if !defined(ML2048_LOAD_MASK)
-            if (kOneHot != ML2048_ONEHOT_NONE) return valid_mask(bd.x, bd.y, bd.z, bd.w);
-#endif
-            return reinterpret_cast<const uint32_t *>(a.valid_in)[g];
-        };
+        const auto current_mask = [&]() -> uint32_t { return mask_now; };
         const uint32_t *sel_row;  // the move's permute selectors (board_ops.cuh)
         if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
             // uniform over the valid directions (policy/random.py:17-27), direction 0 when the game is over: k = floor(u * nvalid)
@@ -331,7 +419,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
             }
                         // step count and score are the halves of ONE 8-byte record per game: one load, one store, one stream
             int2 *const step_score = reinterpret_cast<int2 *>(a.step) + g;
-            const int2 old_ss = *step_score;
+            // a game reset by this very launch starts from step 0, score 0 (its record still holds the finished game's)
+            const int2 old_ss = (kReset && was_reset) ? make_int2(0, 0) : *step_score;
             const float score = __int_as_float(old_ss.y) + (float)gain;
             const int32_t nstep = old_ss.x + 1;
 
@@ -427,7 +516,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads ? kOn
         if (kFull) {  // transition record (REPLAY_SPEC row, replay.py:10-20)
             if (a.tr_state) reinterpret_cast<uint4 *>(a.tr_state)[g] = bd;
             if (a.tr_valid_actions)
-                reinterpret_cast<uint32_t *>(a.tr_valid_actions)[g] = reinterpret_cast<const uint32_t *>(a.valid_in)[g];
+                reinterpret_cast<uint32_t *>(a.tr_valid_actions)[g] =
+                    want_mask ? mask_now : reinterpret_cast<const uint32_t *>(a.valid_in)[g];
             if (a.tr_action) a.tr_action[g] = (int8_t)action;
             if (a.tr_reward) a.tr_reward[g] = tr_reward;
             if (a.tr_next_state) reinterpret_cast<uint4 *>(a.tr_next_state)[g] = out_board;
@@ -520,58 +610,16 @@ __global__ void __launch_bounds__(1024) prepare_scan_kernel(int32_t *tile_counts
     }
 }
 
-// The random inputs of one prepare(): scalar arguments, or the pre-drawn schedule entry a CUDA graph replays.
-struct PrepDraws {
-    int64_t rand_base;
-    uint32_t two_mask;
-    uint64_t philox_counter;
-    const uint8_t *perm_table;
-};
-
-__device__ __forceinline__ PrepDraws load_prep_draws(const ml2048_prepare_args &a)
-{
-    PrepDraws d{a.rand_base, a.two_mask, a.philox_counter, a.randperm};
-    if (a.sched) {
-        const ml2048_sched_entry e = a.sched[*a.sched_cursor];
-        d.rand_base = e.rand_base;
-        d.two_mask = e.two_mask;
-        d.philox_counter = e.philox_counter;
-        d.perm_table += (int64_t)e.table * a.table_stride;
-    }
-    return d;
-}
-
 // The reset body of VecGame.prepare for ONE slot (game_numba.py:634-656): zero the record, id = id_base + order (the
 // rank of the slot among all slots reset by this call: slot-ordered like :641-644), two spawned tiles, the mask.
 // Returns the fresh board.
 template <int kRng>
 __device__ __forceinline__ uint4 reset_slot(const ml2048_prepare_args &a, const PrepDraws &d, int64_t g, int64_t order, int64_t id_base)
 {
-    const uint64_t slot = (uint64_t)(a.slot_base + g);
-    uint32_t c0, c1, v0, v1;
-    if (kRng == ML2048_RNG_REPLAY) {
-        // the board is empty, so the first two entries of the table row are taken (game_numba.py:648-655)
-        const uint32_t row = (uint32_t)((uint64_t)(d.rand_base + (int64_t)slot) % (uint64_t)kRandRows);
-        const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(d.perm_table) + row * 4);
-        c0 = p & 0xffu;
-        c1 = (p >> 8) & 0xffu;
-        v0 = 2u - ((d.two_mask >> (c0 & 15u)) & 1u);
-        v1 = 2u - ((d.two_mask >> (c1 & 15u)) & 1u);
-    } else {
-        // two distinct uniform cells; values by the epoch's per-cell mask, like the reference's reset (:648-655 with :207)
-        const u32x2 rnd = slot_draws(slot, d.philox_counter, a.philox_seed, kResetStream);
-        c0 = rnd.x >> 28;
-        c1 = umulhi32(rnd.y, 15u);
-        c1 += (c1 >= c0) ? 1u : 0u;
-        v0 = 2u - ((d.two_mask >> c0) & 1u);
-        v1 = 2u - ((d.two_mask >> c1) & 1u);
-    }
-    uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u;
-    put_cell(r0, r1, r2, r3, c0 & 15u, v0);
-    put_cell(r0, r1, r2, r3, c1 & 15u, v1);
-    const uint4 bd = make_uint4(r0, r1, r2, r3);
+    uint32_t fresh_mask;
+    const uint4 bd = fresh_board<kRng>(d, (uint64_t)(a.slot_base + g), a.philox_seed, fresh_mask);
     reinterpret_cast<uint4 *>(a.board)[g] = bd;
-    reinterpret_cast<uint32_t *>(a.valid)[g] = valid_mask(r0, r1, r2, r3);
+    reinterpret_cast<uint32_t *>(a.valid)[g] = fresh_mask;
     a.id[g] = (int32_t)(id_base + order);
     reinterpret_cast<int2 *>(a.step)[g] = make_int2(0, 0);  // step = 0, score = 0.0f: one store
     a.reward[g] = 0.0f;
@@ -805,6 +853,92 @@ __global__ void __launch_bounds__(kPrepThreads, 5) prepare_fused_kernel(const ml
     }
 }
 
+// ---- fused auto-reset: bookkeeping kernels ----------------------------------------------------
+
+constexpr int kScanThreads = 1024;  // groups per chunk
+
+// One launch over the `terminated` flags (1 byte per game, the authoritative record of which games are over): thread i
+// counts the finished games of slots [32i, 32i+32) (two 16-byte loads), every block scans its chunk of 1024 such group counts
+// (reset_rank = exclusive prefix inside the chunk) and posts the chunk total; the block that finishes LAST (ticket) scans the chunk totals into reset_chunk_base and advances the id counter.
+// scratch: [0, chunks) chunk totals, [chunks] ticket (zero between launches), [chunks + 1] unused.
+__global__ void __launch_bounds__(kScanThreads) autoreset_scan_kernel(const uint4 *term16, int64_t n16, int32_t *reset_rank,
+                                                                      int32_t *reset_chunk_base, int64_t groups, int64_t *game_count,
+                                                                      const int64_t *id_offset, int64_t *reset_id_base,
+                                                                      int64_t *reset_count, int32_t *scratch)
+{
+    __shared__ int warp_tot[kScanThreads / 32];
+    __shared__ int carry_s;
+    __shared__ bool last_s;
+    const int chunks = (int)gridDim.x;
+    const int64_t i = (int64_t)blockIdx.x * kScanThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int v = 0;
+    if (i < groups) {
+        v = __popc(flags16(term16[2 * i]));
+        if (2 * i + 1 < n16) v += __popc(flags16(term16[2 * i + 1]));  // the padding stops at a multiple of 16 flags
+    }
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 32 warp totals
+        const int t = warp_tot[lane];
+        int w = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += n;
+        }
+        warp_tot[lane] = w - t;
+        if (lane == 31) carry_s = w;  // chunk total
+    }
+    __syncthreads();
+    if (i < groups) reset_rank[i] = warp_tot[warp] + inc - v;
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = carry_s;
+        __threadfence();
+        last_s = atomicAdd(&scratch[chunks], 1) == chunks - 1;
+    }
+    __syncthreads();
+    if (!last_s) return;
+    // the last block: exclusive scan over the chunk totals (volatile reads: they were written by other blocks)
+    __threadfence();
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const volatile int32_t *totals = scratch;
+    for (int base = 0; base < chunks; base += kScanThreads) {
+        const int c = base + threadIdx.x;
+        const int t = c < chunks ? totals[c] : 0;
+        int w = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += n;
+        }
+        if (lane == 31) warp_tot[warp] = w;
+        __syncthreads();
+        int wbase = 0;
+        for (int k = 0; k < warp; ++k) wbase += warp_tot[k];
+        const int carry = carry_s;
+        if (c < chunks) reset_chunk_base[c] = carry + wbase + w - t;
+        __syncthreads();
+        if (threadIdx.x == kScanThreads - 1) carry_s = carry + wbase + w;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int64_t total = carry_s;
+        const int64_t base = *game_count + (id_offset ? *id_offset : 0);
+        *reset_id_base = base;
+        if (!id_offset) *game_count = base + total;
+        *reset_count = total;
+        scratch[chunks] = 0;  // ticket for the next launch
+    }
+}
+
 // ---- small stand-alone ops ------------------------------------------------------------------
 
 template <int kDtype>
@@ -953,7 +1087,7 @@ inline int current_device_slot()
     return (dev >= 0 && dev < kMaxDevices) ? dev : -1;
 }
 
-template <int kRng, bool kLog, bool kFull>
+template <int kRng, bool kLog, bool kFull, bool kReset>
 int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
 {
     // large batches: 768-thread blocks (one contiguous 768 KiB fp32 tile each); medium batches 256-thread blocks; small
@@ -978,22 +1112,22 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
         static bool opted_in[kMaxDevices];                                                             \
         const int dev_slot = current_device_slot();                                                    \
         if (dev_slot < 0 || !opted_in[dev_slot]) {                                                     \
-            const cudaError_t e = cudaFuncSetAttribute(step_kernel<kRng, kLog, OH, kFull, T>,           \
+            const cudaError_t e = cudaFuncSetAttribute(step_kernel<kRng, kLog, OH, kFull, T, kReset>,   \
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
             if (e != cudaSuccess) return (int)e;                                                       \
             if (dev_slot >= 0) opted_in[dev_slot] = true;                                              \
         }                                                                                              \
-        step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, smem, s>>>(a);                             \
-    } else if (small) step_kernel<kRng, kLog, OH, kFull, S><<<grid_small, S, 0, s>>>(a);                \
-    else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
+        step_kernel<kRng, kLog, OH, kFull, T, kReset><<<grid_big, T, smem, s>>>(a);                     \
+    } else if (small) step_kernel<kRng, kLog, OH, kFull, S, kReset><<<grid_small, S, 0, s>>>(a);        \
+    else step_kernel<kRng, kLog, OH, kFull, kStepThreads, kReset><<<grid, kStepThreads, 0, s>>>(a)
 #else
 #define ML2048_LAUNCH(OH)                                                                              \
-    if (big) step_kernel<kRng, kLog, OH, kFull, T><<<grid_big, T, 0, s>>>(a);                           \
-    else if (small) step_kernel<kRng, kLog, OH, kFull, S><<<grid_small, S, 0, s>>>(a);                  \
-    else step_kernel<kRng, kLog, OH, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a)
+    if (big) step_kernel<kRng, kLog, OH, kFull, T, kReset><<<grid_big, T, 0, s>>>(a);                   \
+    else if (small) step_kernel<kRng, kLog, OH, kFull, S, kReset><<<grid_small, S, 0, s>>>(a);          \
+    else step_kernel<kRng, kLog, OH, kFull, kStepThreads, kReset><<<grid, kStepThreads, 0, s>>>(a)
 #endif
     switch (onehot) {
-    case ML2048_ONEHOT_NONE: step_kernel<kRng, kLog, ML2048_ONEHOT_NONE, kFull, kStepThreads><<<grid, kStepThreads, 0, s>>>(a); break;
+    case ML2048_ONEHOT_NONE: step_kernel<kRng, kLog, ML2048_ONEHOT_NONE, kFull, kStepThreads, kReset><<<grid, kStepThreads, 0, s>>>(a); break;
     case ML2048_ONEHOT_F32: ML2048_LAUNCH(ML2048_ONEHOT_F32); break;
     case ML2048_ONEHOT_BF16: ML2048_LAUNCH(ML2048_ONEHOT_BF16); break;
     default: ML2048_LAUNCH(ML2048_ONEHOT_U8); break;
@@ -1007,8 +1141,13 @@ int launch_step(const ml2048_step_args &a, cudaStream_t s)
 {
     const bool full = a.action_mode == ML2048_ACTIONS_FROM_LOGITS || a.episode_max_tile || a.traj_state || a.tr_state || a.tr_valid_actions ||
                       a.tr_action || a.tr_reward || a.tr_next_state || a.tr_next_valid_actions || a.tr_step || a.tr_terminated;
-    if (full) return a.merged ? launch_step_onehot<kRng, true, true>(a, s) : launch_step_onehot<kRng, false, true>(a, s);
-    return a.merged ? launch_step_onehot<kRng, true, false>(a, s) : launch_step_onehot<kRng, false, false>(a, s);
+    if (a.reset_rank) {
+        // the fused auto-reset is built for the lean kernels (the synthetic random-policy rollouts it serves)
+        if (full) return ML2048_E_ENUM;
+        return a.merged ? launch_step_onehot<kRng, true, false, true>(a, s) : launch_step_onehot<kRng, false, false, true>(a, s);
+    }
+    if (full) return a.merged ? launch_step_onehot<kRng, true, true, false>(a, s) : launch_step_onehot<kRng, false, true, false>(a, s);
+    return a.merged ? launch_step_onehot<kRng, true, false, false>(a, s) : launch_step_onehot<kRng, false, false, false>(a, s);
 }
 
 }  // namespace
@@ -1066,6 +1205,14 @@ int ml2048_step(const ml2048_step_args *args, void *stream)
     if (a.sched) {
         if (!a.sched_cursor || a.sched_cursor == a.sched_cursor_next) return ML2048_E_NULL;
         if (misaligned(a.sched, 8) || misaligned(a.sched_cursor, 8) || misaligned(a.sched_cursor_next, 8) || (a.table_stride & 15))
+            return ML2048_E_ALIGN;
+    }
+    if (a.reset_rank) {
+        if (a.action_mode != ML2048_ACTIONS_RANDOM_VALID) return ML2048_E_ENUM;  // given actions belong to post-reset observations
+        if (!a.reset_chunk_base || !a.reset_id_base || !a.id || !a.valid_in) return ML2048_E_NULL;
+        if (a.rng_mode == ML2048_RNG_REPLAY && !a.randperm) return ML2048_E_NULL;
+        if (misaligned(a.reset_rank, 4) || misaligned(a.reset_chunk_base, 4) || misaligned(a.reset_id_base, 8) ||
+            misaligned(a.reset_indices, 8) || misaligned(a.randperm, 16) || misaligned(a.id, 4))
             return ML2048_E_ALIGN;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1208,6 +1355,31 @@ int ml2048_prepare(const ml2048_prepare_args *args, void *stream)
     rc = ml2048_prepare_count(args, stream);
     if (rc) return rc;
     return ml2048_prepare_apply(args, stream);
+}
+
+int64_t ml2048_autoreset_scratch_ints(int64_t num_games)
+{
+    if (num_games <= 0) return 0;
+    const int64_t groups = (num_games + 31) / 32;
+    return (groups + kScanThreads - 1) / kScanThreads + 2;
+}
+
+int ml2048_autoreset_scan(const uint8_t *terminated, int32_t *reset_rank, int32_t *reset_chunk_base, int64_t num_games, int64_t *game_count,
+                          const int64_t *id_offset, int64_t *reset_id_base, int64_t *reset_count, int32_t *scratch, void *stream)
+{
+    if (num_games <= 0) return ML2048_E_SIZE;
+    if (!terminated || !reset_rank || !reset_chunk_base || !game_count || !reset_id_base || !reset_count || !scratch) return ML2048_E_NULL;
+    if (misaligned(terminated, 16) || misaligned(reset_rank, 4) || misaligned(reset_chunk_base, 4) || misaligned(game_count, 8) ||
+        misaligned(id_offset, 8) || misaligned(reset_id_base, 8) || misaligned(reset_count, 8) || misaligned(scratch, 4))
+        return ML2048_E_ALIGN;
+    const int64_t groups = (num_games + 31) / 32;
+    const unsigned chunks = (unsigned)((groups + kScanThreads - 1) / kScanThreads);
+    clear_stale_error();
+    autoreset_scan_kernel<<<chunks, kScanThreads, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4 *>(terminated),
+                                                                                        (num_games + 15) / 16, reset_rank, reset_chunk_base, groups,
+                                                                                        game_count, id_offset, reset_id_base, reset_count,
+                                                                                        scratch);
+    return launch_status();
 }
 
 int ml2048_reset_state(void *board_a, void *board_b, void *valid_a, void *valid_b, int32_t *id, int32_t *step, float *score,

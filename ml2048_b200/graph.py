@@ -26,9 +26,12 @@ class GraphedRollout:
     (run_train3.py:175-183) becomes one graph launch."""
 
     def __init__(self, env: VecGame, steps: int, *, window: Optional[int] = None, actions: Optional[torch.Tensor] = None,
-                 return_actions: bool = False, logits_fn: Any = None, buffers: Any = None, use_index: int = 0):
+                 return_actions: bool = False, logits_fn: Any = None, buffers: Any = None, use_index: int = 0,
+                 auto_reset: bool = False):
         if steps <= 0 or steps % 2:
             raise ValueError(f"steps={steps}: must be a positive even number")
+        if auto_reset and (logits_fn is not None or actions is not None or buffers is not None):
+            raise ValueError("auto_reset=True fuses prepare() into step_random(): in-kernel random policy only, no buffers")
         self.env, self.steps = env, int(steps)
         self.window = int(window) if window else self.steps * 16
         if self.window < self.steps:
@@ -53,8 +56,13 @@ class GraphedRollout:
                         logits_fn(env)
                 side.synchronize()
             env._skip_id_check = True  # the id-range accounting is done per replay() (no device reads while capturing)
+            if auto_reset:
+                env._ensure_autoreset()  # allocate outside the capture
             with torch.cuda.graph(self.graph, stream=side):
                 for t in range(self.steps):
+                    if auto_reset:
+                        env.step_random(return_actions=return_actions, auto_reset=True)
+                        continue
                     env.prepare()
                     record = buffers.row(use_index, t) if buffers is not None else None
                     if logits_fn is not None:

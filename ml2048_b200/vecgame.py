@@ -343,6 +343,7 @@ class VecGame:
         self._dist_world = 1
         self._id_bound = None
         self._skip_id_check = False
+        self._reset_rank = None
 
         self._step_args = _lib.StepArgs()
         self._prep_args = _lib.PrepareArgs()
@@ -678,20 +679,9 @@ class VecGame:
             p.sched_cursor = self._cursor_ptr[cur]
             p.table_stride = self._TABLE_BYTES
         else:
-            rand_offset = 0
-            if self._rng_mode == _lib.RNG_REPLAY:  # Philox spawns need none of the reference's host draws
-                if self._draw_coin() >= 0.9 or self._rand_step >= self._RAND_SIZE:
-                    self._rand_step = 0
-                    self._schedule.refresh_tables(self._randperm, self._randfloat)
-                    self._upload_tables()
-                rand_offset = self._schedule.offset()
-            else:
-                self._philox_epoch(self._philox_counter)
             p.sched = None
-            p.rand_base = self._rand_step + rand_offset
+            p.rand_base, p.philox_counter = self._prepare_draws()
             p.two_mask = self._two_mask
-            p.philox_counter = self._philox_counter
-            self._philox_counter += 1
         p.board = self._board_ptr[cur]
         p.valid = self._valid_ptr[cur]
         p.randperm = self._table_ptrs()[0]
@@ -725,6 +715,22 @@ class VecGame:
         if n == 0:
             return (np.zeros((0,), dtype=np.int64),)
         return (idx.cpu().numpy(),)
+
+    def _prepare_draws(self) -> tuple[int, int]:
+        """The host half of one eager prepare() (game_numba.py:622-626): refresh the tables with probability 0.1, draw the
+        row offset.  Returns (rand_base, the Philox counter this prepare uses)."""
+        rand_offset = 0
+        if self._rng_mode == _lib.RNG_REPLAY:  # Philox spawns need none of the reference's host draws
+            if self._draw_coin() >= 0.9 or self._rand_step >= self._RAND_SIZE:
+                self._rand_step = 0
+                self._schedule.refresh_tables(self._randperm, self._randfloat)
+                self._upload_tables()
+            rand_offset = self._schedule.offset()
+        else:
+            self._philox_epoch(self._philox_counter)
+        counter = self._philox_counter
+        self._philox_counter += 1
+        return self._rand_step + rand_offset, counter
 
     _COIN_REFRESH = int(0.9 * 4294967296.0)  # a 32-bit coin >= this value opens a new table epoch (game_numba.py:622)
 
@@ -919,23 +925,74 @@ class VecGame:
     # extras: device-side policy for synthetic rollouts, statistics, sharding
     # ------------------------------------------------------------------------------------------
 
-    def step_random(self, *, return_actions: bool = False, record: Optional[dict] = None):
+    def step_random(self, *, return_actions: bool = False, record: Optional[dict] = None, auto_reset: bool = False):
         """One step with uniformly random VALID actions chosen inside the kernel (Philox) --
-        the benchmark policy (semantics of policy/random.py:17-27), no action array crosses the bus."""
+        the benchmark policy (semantics of policy/random.py:17-27), no action array crosses the bus.
+
+        ``auto_reset=True`` fuses the preceding ``prepare()`` into the same launch: the games that are over are reset
+        first (slot-ordered ids, two tiles, the reference's draws in the reference's order) and then played.  Every
+        array ends up exactly as after ``prepare(); step_random()`` -- including ``prev_state`` -- but the scattered
+        writes of the reset ride on the step's coalesced ones and one launch (plus a 1-block-per-32k-games scan of the
+        finished-game counts the previous step published) replaces two.  ``last_reset()`` returns what ``prepare()``
+        would have returned."""
         a = self._step_args
         a.action_mode = _lib.ACTIONS_RANDOM_VALID
         a.action_dtype = _lib.ACT_U8
         a.actions = None
         a.actions_out = self._p(self._actions_out) if return_actions else None
         self._set_record(record)
-        self._launch_step()
+        self._launch_step(fused_reset=auto_reset)
         return VecStepResult(self)
 
-    def _launch_step(self) -> None:
+    def last_reset(self):
+        """``(indices,)`` of the games the last prepare() / step_random(auto_reset=True) reset (synchronises)."""
+        n = int(self._reset_count_dev.item())
+        idx = self._reset_indices_dev[:n]
+        return (idx if self._output == "torch" else idx.cpu().numpy(),)
+
+    def _ensure_autoreset(self) -> None:
+        """Buffers of the fused auto-reset (allocated on first use): the slot-ordered ranks of the finished games, which
+        ml2048_autoreset_scan derives from the `terminated` flags right before a fused step."""
+        if getattr(self, "_reset_rank", None) is not None:
+            return
+        groups = (self._size + 31) // 32
+        chunks = (groups + 1023) // 1024
+        dev = self.device
+        self._reset_rank = torch.zeros((groups,), dtype=torch.int32, device=dev)
+        self._reset_chunk_base = torch.zeros((chunks,), dtype=torch.int32, device=dev)
+        self._reset_id_base = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self._ar_scratch = torch.zeros((int(self._lib.ml2048_autoreset_scratch_ints(self._size)),), dtype=torch.int32, device=dev)
+        self._step_args.id = self._p(self._id)
+
+    def _launch_autoreset_scan(self, stream: int) -> None:
+        _lib.check(self._lib.ml2048_autoreset_scan(self._p(self._terminated_padded), self._reset_rank.data_ptr(),
+                                                   self._reset_chunk_base.data_ptr(), self._size, self._p(self._game_count_dev), None,
+                                                   self._reset_id_base.data_ptr(), self._p(self._reset_count_dev),
+                                                   self._ar_scratch.data_ptr(), stream), "ml2048_autoreset_scan")
+
+    def _launch_step(self, fused_reset: bool = False) -> None:
         a = self._step_args
         cur = self._cur
         self._obs_cache = None
         self._state_epoch += 1
+        if fused_reset:
+            if self._dist_group is not None:
+                raise RuntimeError("auto_reset=True is not available with shard() (globally ordered ids need the per-rank counts "
+                                   "between the scan and the step): call prepare() and step_random()")
+            if self._record_active or self._step_args.episode_max_tile or self._step_args.traj_state:
+                raise RuntimeError("auto_reset=True serves the lean kernels: no record=, episode log or trajectory log")
+            self._ensure_autoreset()
+            self._check_id_range(1)
+            if self._sched_len and self._sched_pos >= self._sched_len:
+                self.schedule_ahead(self._sched_len)
+            a.reset_rank = self._reset_rank.data_ptr()
+            a.reset_chunk_base = self._reset_chunk_base.data_ptr()
+            a.reset_id_base = self._reset_id_base.data_ptr()
+            a.reset_indices = self._p(self._reset_indices_dev)
+            if not self._sched_len:
+                a.rand_base, a.prepare_philox_counter = self._prepare_draws()  # prepare()'s host draws come first (:622-626)
+        else:
+            a.reset_rank = None
         if self._sched_len:
             if self._sched_pos >= self._sched_len:
                 raise RuntimeError("the device schedule is used up: call prepare() (or schedule_ahead) first")
@@ -956,10 +1013,13 @@ class VecGame:
         a.board_out = self._board_ptr[1 - cur]
         a.valid_in = self._valid_ptr[cur]
         a.valid_out = self._valid_ptr[1 - cur]
-        a.randperm_keys = self._table_ptrs()[1]
+        a.randperm, a.randperm_keys = self._table_ptrs()
         a.philox_seed = self._philox_seed
+        stream = self._stream()
         with self._guard:
-            _lib.check(self._lib.ml2048_step(C.byref(a), self._stream()), "ml2048_step")
+            if fused_reset:
+                self._launch_autoreset_scan(stream)
+            _lib.check(self._lib.ml2048_step(C.byref(a), stream), "ml2048_step")
         self._cur = 1 - cur
 
     # -- host-buffer pipeline -----------------------------------------------------------------------
@@ -1013,6 +1073,7 @@ class VecGame:
             host[k] = buf
         a = _lib.StepArgs.from_buffer_copy(self._step_args)
         a.action_mode, a.action_dtype, a.actions_out, a.sched = _lib.ACTIONS_GIVEN, code, None, None
+        a.reset_rank = None  # (left over from an earlier step_random(auto_reset=True))
         a.rand_seed, a.two_mask, a.philox_counter, a.philox_seed = rand_seed, self._two_mask, counter, self._philox_seed
         a.randperm_keys = self._table_ptrs()[1]
         esz = actions.element_size()

@@ -84,6 +84,14 @@ void hs_policy_sel_table(uint32_t *out512)
     memcpy(out512, t.w, sizeof(t.w));
 }
 
+// the 1024 boards a reset can produce + their masks: copies 1024 x 4 board words and 1024 mask words
+void hs_fresh_table(uint32_t *boards4096, uint32_t *masks1024)
+{
+    static const FreshTable t = make_fresh_table();
+    memcpy(boards4096, t.board, sizeof(t.board));
+    memcpy(masks1024, t.mask, sizeof(t.mask));
+}
+
 void hs_move_sel_table(uint32_t *out32)
 {
     static const uint32_t base[4 * kMoveSelRow] = ML2048_MOVE_SEL_TABLE;

@@ -203,6 +203,25 @@ def test_policy_selector_table(shim):
     assert [int(tab[60 + a][6]) for a in range(4)] == [0, 1, 2, 3]
 
 
+def test_fresh_board_table(shim, oracle):
+    """Every entry of the reset's lookup table = the two tiles placed with put_cell and the product's (and the oracle's)
+    valid-action mask of that board."""
+    shim.hs_fresh_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    shim.hs_put_cell.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]
+    boards = np.zeros((1024, 16), np.uint8)
+    masks = np.zeros((1024,), np.uint32)
+    shim.hs_fresh_table(boards.ctypes.data, masks.ctypes.data)
+    for idx in range(1024):
+        c0, c1, t0, t1 = idx >> 6, (idx >> 2) & 15, (idx >> 1) & 1, idx & 1
+        b = np.zeros(16, np.uint8)
+        shim.hs_put_cell(b.ctypes.data, c0, 2 - t0)
+        shim.hs_put_cell(b.ctypes.data, c1, 2 - t1)
+        np.testing.assert_array_equal(boards[idx], b)
+        assert int(masks[idx]) == shim.hs_valid_mask(b.ctypes.data), idx
+        if c0 != c1:
+            assert masks[idx : idx + 1].view(np.uint8).tolist() == oracle.board_valid(b).tolist(), idx
+
+
 PHILOX2X32_KAT = [  # Random123 kat_vectors: philox2x32 10
     ((0, 0), 0, (0xFF1DAE59, 0x6CD10DF2)),
     ((0xFFFFFFFF, 0xFFFFFFFF), 0xFFFFFFFF, (0x2C3F628B, 0xAB4FD7AD)),

@@ -19,6 +19,7 @@ p.add_argument("--onehot", default=None)
 p.add_argument("--steps", type=int, default=20)
 p.add_argument("--burn-in", type=int, default=64)
 p.add_argument("--merged", action="store_true")
+p.add_argument("--fused", action="store_true", help="step_random(auto_reset=True): the auto-reset fused into the step kernel")
 a = p.parse_args()
 
 env = ml2048_b200.VecGame(a.games, output="torch", rng_mode=a.rng, onehot=a.onehot, track_merged=a.merged, sync_free=True)
@@ -39,11 +40,18 @@ torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * a.steps)]
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0.record()
+if a.fused:
+    env.step_random(auto_reset=True)  # allocates the bookkeeping buffers, publishes the first counts
+    torch.cuda.synchronize()
+    t0.record()
 for t in range(a.steps):
     ev[3 * t].record()
-    env.prepare()
+    if not a.fused:
+        env.prepare()
     ev[3 * t + 1].record()
-    if acts is None:
+    if a.fused:
+        env.step_random(auto_reset=True)
+    elif acts is None:
         env.step_random()
     else:
         env.step(acts[t])
@@ -53,6 +61,6 @@ torch.cuda.synchronize()
 prep = sum(ev[3 * t].elapsed_time(ev[3 * t + 1]) for t in range(a.steps)) / a.steps
 step = sum(ev[3 * t + 1].elapsed_time(ev[3 * t + 2]) for t in range(a.steps)) / a.steps
 tot = t0.elapsed_time(t1) / a.steps
-print(f"games={a.games} rng={a.rng} actions={a.actions} onehot={a.onehot} merged={a.merged}: prepare {prep*1e3:.1f} us, step {step*1e3:.1f} us, "
+print(f"games={a.games} rng={a.rng} actions={a.actions} onehot={a.onehot} merged={a.merged} fused_reset={a.fused}: prepare {prep*1e3:.1f} us, step {step*1e3:.1f} us, "
       f"total {tot*1e3:.1f} us/step -> {a.games/tot/1e6:.2f} G env-steps/s; step kernel alone {a.games/step/1e6:.2f} G/s "
       f"= {59*a.games/step/1e6/6543.1*100:.1f}% of HBM peak at 59 B/step")
