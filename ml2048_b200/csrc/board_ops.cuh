@@ -470,15 +470,17 @@ ML2048_FN u32x2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k)
 }
 
 // The two uniform words of global slot `slot` at counter `counter` of stream `tag` (0 = step, kResetStream = auto-reset):
-// counter = (slot low word, counter low word); key = seed, the high words and the tag folded together (all but the slot's
-// high word are uniform over the launch, i.e. computed once per warp on the uniform datapath).
+// Philox counter = (slot low word, counter low word ^ high words * odd constants); key = seed ^ tag.  The key depends on
+// nothing but the seed (a kernel parameter), so its ten round values are computed once per warp on the uniform datapath --
+// the step counter may come from a device-resident schedule entry, i.e. from a vector register, and a key built from it
+// costs nine ALU adds per game-step.
 constexpr uint32_t kResetStream = 0x80000000u;
 
 ML2048_FN u32x2 slot_draws(uint64_t slot, uint64_t counter, uint64_t seed, uint32_t tag)
 {
-    const uint32_t key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ ((uint32_t)(counter >> 32) * 0x85EBCA6Bu) ^
-                         ((uint32_t)(slot >> 32) * 0xC2B2AE35u) ^ tag;
-    return philox2x32_10((uint32_t)slot, (uint32_t)counter, key);
+    const uint32_t key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ tag;
+    const uint32_t c1 = (uint32_t)counter ^ ((uint32_t)(counter >> 32) * 0x85EBCA6Bu) ^ ((uint32_t)(slot >> 32) * 0xC2B2AE35u);
+    return philox2x32_10((uint32_t)slot, c1, key);
 }
 
 // Masked categorical sample (policy/actor_critic.py:56-76): invalid actions get finfo.min, the logits are

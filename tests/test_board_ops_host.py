@@ -239,11 +239,12 @@ def test_philox2x32_known_answers(shim):
 
 
 def test_slot_draws_key_schedule(shim):
-    """slot_draws = Philox2x32-10 with counter (slot low, counter low) and the seed / high words / stream tag folded into the key."""
+    """slot_draws = Philox2x32-10 with counter (slot low, counter low ^ high words * odd constants) and key = seed ^ stream tag
+    (uniform over a launch)."""
     def ref(slot, counter, seed, tag):
         m = 0xFFFFFFFF
-        key = (seed & m) ^ (((seed >> 32) * 0x9E3779B9) & m) ^ (((counter >> 32) * 0x85EBCA6B) & m) ^ (((slot >> 32) * 0xC2B2AE35) & m) ^ tag
-        c = np.array([slot & m, counter & m], np.uint32)
+        key = (seed & m) ^ (((seed >> 32) * 0x9E3779B9) & m) ^ tag
+        c = np.array([slot & m, (counter & m) ^ (((counter >> 32) * 0x85EBCA6B) & m) ^ (((slot >> 32) * 0xC2B2AE35) & m)], np.uint32)
         out = np.zeros(2, np.uint32)
         shim.hs_philox2(c.ctypes.data, key, out.ctypes.data)
         return tuple(int(x) for x in out)

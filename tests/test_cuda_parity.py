@@ -717,9 +717,9 @@ def test_device_draws_equal_host_philox2x32(ml):
         want = np.empty(m, np.uint8)
         for g in range(m):
             slot = base + g
-            key = (seed & mask32) ^ (((seed >> 32) * 0x9E3779B9) & mask32) ^ (((counter >> 32) * 0x85EBCA6B) & mask32) \
-                ^ (((slot >> 32) * 0xC2B2AE35) & mask32)
-            c = np.array([slot & mask32, counter & mask32], np.uint32)
+            key = (seed & mask32) ^ (((seed >> 32) * 0x9E3779B9) & mask32)
+            c = np.array([slot & mask32, (counter & mask32) ^ (((counter >> 32) * 0x85EBCA6B) & mask32)
+                          ^ (((slot >> 32) * 0xC2B2AE35) & mask32)], np.uint32)
             lib.ml2048_philox2x32_10(c.ctypes.data, key, out2.ctypes.data)
             want[g] = int(out2[1]) >> 30
         np.testing.assert_array_equal(got, want)
