@@ -232,8 +232,11 @@ __device__ const FreshTable d_fresh = make_fresh_table();
 
 // The two tiles a reset spawns on the empty board (game_numba.py:648-655 with :207): replay mode takes the first two
 // entries of the slot's table row, Philox mode two distinct uniform cells; 2 or 4 by the table epoch's per-cell mask.
-// Returns the board and (in `mask`) its valid-action word, both looked up.
-template <int kRng>
+// Returns the board and (in `mask`) its valid-action word.  kLookup: both come from the 1024-entry table (the fused
+// auto-reset inside the step kernel, where the reset path's LENGTH is what costs); otherwise they are computed (the
+// stand-alone prepare kernels: a single latency-bound block at the training shape, where two more dependent loads from a
+// cold 20 KiB table cost 0.3 us per step).
+template <int kRng, bool kLookup>
 __device__ __forceinline__ uint4 fresh_board(const PrepDraws &d, uint64_t slot, uint64_t philox_seed, uint32_t &mask)
 {
     uint32_t c0, c1;
@@ -248,9 +251,17 @@ __device__ __forceinline__ uint4 fresh_board(const PrepDraws &d, uint64_t slot, 
         c1 = umulhi32(rnd.y, 15u);
         c1 += (c1 >= c0) ? 1u : 0u;
     }
-    const uint32_t idx = (c0 << 6) | (c1 << 2) | (((d.two_mask >> c0) & 1u) << 1) | ((d.two_mask >> c1) & 1u);
-    mask = __ldg(d_fresh.mask + idx);
-    return __ldg(reinterpret_cast<const uint4 *>(d_fresh.board) + idx);
+    const uint32_t t0 = (d.two_mask >> c0) & 1u, t1 = (d.two_mask >> c1) & 1u;  // 1: the tile is a 2, 0: a 4 (game_numba.py:207)
+    if (kLookup) {
+        const uint32_t idx = (c0 << 6) | (c1 << 2) | (t0 << 1) | t1;
+        mask = __ldg(d_fresh.mask + idx);
+        return __ldg(reinterpret_cast<const uint4 *>(d_fresh.board) + idx);
+    }
+    uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u;
+    put_cell(r0, r1, r2, r3, c0, 2u - t0);
+    put_cell(r0, r1, r2, r3, c1, 2u - t1);
+    mask = valid_mask(r0, r1, r2, r3);
+    return make_uint4(r0, r1, r2, r3);
 }
 
 // ---- the step kernel ------------------------------------------------------------------------
@@ -346,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
                 d.philox_counter = e.philox_counter;
                 d.perm_table += (int64_t)e.table * a.table_stride;
             }
-            bd = fresh_board<kRng>(d, (uint64_t)(a.slot_base + g), a.philox_seed, mask_now);
+            bd = fresh_board<kRng, true>(d, (uint64_t)(a.slot_base + g), a.philox_seed, mask_now);
             // prev_state / prev_valid_actions of this step are the post-reset board and mask (game_numba.py:672-673)
             reinterpret_cast<uint4 *>(const_cast<void *>(a.board_in))[g] = bd;
             reinterpret_cast<uint32_t *>(const_cast<void *>(a.valid_in))[g] = mask_now;
@@ -369,8 +380,16 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
             // uniform over the valid directions (policy/random.py:17-27), direction 0 when the game is over: k = floor(u * nvalid)
             // indexes the (mask, k) table, whose row carries the selectors AND the direction -- no search for the k-th set bit
             const uint32_t bits = mask_bits4(current_mask());
-            sel_row = d_policy_sel.w + (bits * 4u + umulhi32(rnd.y, popc32(bits))) * kMoveSelRow;
-            action = 0u;  // read from the row below
+            const uint32_t kth = umulhi32(rnd.y, popc32(bits));
+            if (kThreads == kSmallStepThreads) {
+                // small batches are latency-bound: the 2 KiB table costs a few more cold L1 lines per block than it saves in
+                // issue slots (8.2 vs 8.5 us per step at M = 2048 in a CUDA graph), so they search the k-th set bit
+                action = bits ? kth_valid_action(bits, kth) : 0u;
+                sel_row = d_move_sel + action * kMoveSelRow;
+            } else {
+                sel_row = d_policy_sel.w + (bits * 4u + kth) * kMoveSelRow;
+                action = 0u;  // read from the row below
+            }
         } else if (kFull && a.action_mode == ML2048_ACTIONS_FROM_LOGITS) {
             const uint32_t bits = mask_bits4(current_mask());
             const float4 lg = reinterpret_cast<const float4 *>(a.logits)[g];
@@ -391,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
         uint32_t tr_term = 0u, tr_mask = 0u;
         const uint32_t row_action = move_board_sel(r0, r1, r2, r3, sel_row, f);
         if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
-            action = row_action;
+            if (kThreads != kSmallStepThreads) action = row_action;
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
         }
         // valid_actions[action] (game_numba.py:718) == "the move changes the board"; out-of-range
@@ -617,7 +636,7 @@ template <int kRng>
 __device__ __forceinline__ uint4 reset_slot(const ml2048_prepare_args &a, const PrepDraws &d, int64_t g, int64_t order, int64_t id_base)
 {
     uint32_t fresh_mask;
-    const uint4 bd = fresh_board<kRng>(d, (uint64_t)(a.slot_base + g), a.philox_seed, fresh_mask);
+    const uint4 bd = fresh_board<kRng, false>(d, (uint64_t)(a.slot_base + g), a.philox_seed, fresh_mask);
     reinterpret_cast<uint4 *>(a.board)[g] = bd;
     reinterpret_cast<uint32_t *>(a.valid)[g] = fresh_mask;
     a.id[g] = (int32_t)(id_base + order);
