@@ -561,6 +561,183 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
     }
 }
 
+// ---- the lean step kernel, two games per thread ---------------------------------------------
+// The core-only step (no one-hot, no `merged`, none of the rollout extras) is bound by the integer ALU pipe, and a good
+// part of what it issues there is not game arithmetic: two instructions of address arithmetic for each of nine arrays, the
+// bounds checks, the predicates of the schedule.  A thread that owns TWO ADJACENT games computes every address once (the
+// second game sits at an immediate offset), shares the prologue, and gives the scheduler two independent instruction
+// streams.  Same arithmetic per game as step_kernel (the same board_ops.cuh functions in the same order), same draws (one
+// Philox2x32-10 block per game-step keyed by the global slot), so every array is bit-identical to the one-game-per-thread
+// kernel (tests/test_pair_kernel.py); large batches of the lean configuration are routed here by launch_step.
+// Measured at M = 2^24 (auto-reset fused, random policy / given actions, us per launch; one-game-per-thread kernel: 274.6 / 231):
+// 256 threads x 5 blocks (48 registers) 274.7 / 230.9, x 4 (64) 278.2 / 240.0, x 6 (40) 270.9 / 225.2, x 8 (32, spills) 276.1 / 232.4;
+// 128 threads x 8 (64) 270.4 / 227.9, x 10 (48) 273.0 / 226.8, x 12 (40 registers) 269.4 / 222.2.
+#ifndef ML2048_PAIR_THREADS
+#define ML2048_PAIR_THREADS 128
+#endif
+#ifndef ML2048_PAIR_MIN_BLOCKS
+#define ML2048_PAIR_MIN_BLOCKS 12
+#endif
+constexpr int kPairThreads = ML2048_PAIR_THREADS;
+constexpr int64_t kPairMinGames = 1 << 17;  // below this the batch is latency-bound: more, smaller threads win
+
+template <int kRng, bool kReset>
+__global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pair_kernel(const ml2048_step_args a)
+{
+    const int64_t g0 = ((int64_t)blockIdx.x * kPairThreads + threadIdx.x) * 2;  // this thread owns games g0 and g0 + 1
+    if (g0 >= a.num_games) return;
+    const bool live1 = g0 + 1 < a.num_games;
+
+    int64_t rand_seed = a.rand_seed;
+    uint32_t two_mask = a.two_mask;
+    uint64_t philox_counter = a.philox_counter;
+    const uint8_t *keys_table = a.randperm_keys;
+    if (a.sched) {
+        const int64_t cursor = *a.sched_cursor;
+        const ml2048_sched_entry e = a.sched[cursor];
+        rand_seed = e.rand_seed;
+        two_mask = e.two_mask;
+        philox_counter = e.philox_counter + 1ull;
+        keys_table += (int64_t)e.table * a.table_stride;
+        if (a.sched_cursor_next && blockIdx.x == 0 && threadIdx.x == 0) *a.sched_cursor_next = cursor + 1;
+    }
+
+    // one address per array; the second game of the pair is the next element
+    const uint4 *board_in = reinterpret_cast<const uint4 *>(a.board_in) + g0;
+    uint4 *board_out = reinterpret_cast<uint4 *>(a.board_out) + g0;
+    uint32_t *valid_out = reinterpret_cast<uint32_t *>(a.valid_out) + g0;
+    int2 *step_score = reinterpret_cast<int2 *>(a.step) + g0;
+    float *reward_out = a.reward + g0;
+    uint8_t *terminated = a.terminated + g0, *invalid = a.invalid + g0;
+
+    uint4 bd[2];
+    bd[0] = board_in[0];
+    bd[1] = live1 ? board_in[1] : make_uint4(0, 0, 0, 0);
+    const bool want_mask = kReset || a.action_mode != ML2048_ACTIONS_GIVEN;
+    uint32_t mask_now[2] = {1u, 1u};
+    if (want_mask) {
+        const uint32_t *valid_in = reinterpret_cast<const uint32_t *>(a.valid_in) + g0;
+        mask_now[0] = valid_in[0];
+        if (live1) mask_now[1] = valid_in[1];
+    }
+    int2 ss[2];
+    ss[0] = step_score[0];
+    ss[1] = live1 ? step_score[1] : make_int2(0, 0);
+
+    if (kReset) {
+        // fused auto-reset (see step_kernel): lane l holds slots 2l and 2l+1 of the warp's 64, i.e. of TWO 32-slot groups
+        // of the scan; ranks count the finished games of the lower lanes of the same half-warp, both games of each
+        const bool over0 = mask_now[0] == 0u, over1 = live1 && mask_now[1] == 0u;
+        const uint32_t lanes0 = __ballot_sync(0xffffffffu, over0), lanes1 = __ballot_sync(0xffffffffu, over1);
+        if (over0 || over1) {
+            const uint32_t lane = threadIdx.x & 31u;
+            const uint32_t lower = ((1u << lane) - 1u) & (0xffffu << (lane & 16u));
+            const uint32_t group = (uint32_t)g0 >> 5;
+            int32_t order = __ldg(a.reset_chunk_base + (group >> 10)) + __ldg(a.reset_rank + group) + __popc(lanes0 & lower) +
+                            __popc(lanes1 & lower);
+            PrepDraws d{a.rand_base, two_mask, a.prepare_philox_counter, a.randperm};
+            if (a.sched) {
+                const ml2048_sched_entry e = a.sched[*a.sched_cursor];
+                d.rand_base = e.rand_base;
+                d.philox_counter = e.philox_counter;
+                d.perm_table += (int64_t)e.table * a.table_stride;
+            }
+            const int32_t id_base = (int32_t)*a.reset_id_base;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j == 0 ? over0 : over1) {
+                    bd[j] = fresh_board<kRng, true>(d, (uint64_t)(a.slot_base + g0 + j), a.philox_seed, mask_now[j]);
+                    reinterpret_cast<uint4 *>(const_cast<void *>(a.board_in))[g0 + j] = bd[j];
+                    reinterpret_cast<uint32_t *>(const_cast<void *>(a.valid_in))[g0 + j] = mask_now[j];
+                    a.id[g0 + j] = id_base + order;
+                    if (a.reset_indices && (int64_t)order < a.num_games) a.reset_indices[order] = g0 + j;
+                    if (a.age) a.age[g0 + j] = 0;
+                    ss[j] = make_int2(0, 0);
+                    order += 1;
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (j == 1 && !live1) break;
+        const int64_t g = g0 + j;
+        const uint64_t slot = (uint64_t)(a.slot_base + g);
+        u32x2 rnd = {0u, 0u};
+        if (kRng == ML2048_RNG_PHILOX || a.action_mode != ML2048_ACTIONS_GIVEN) rnd = slot_draws(slot, philox_counter, a.philox_seed, 0u);
+        uint32_t action = 0u;
+        const uint32_t *sel_row;
+        if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
+            const uint32_t bits = mask_bits4(mask_now[j]);
+            sel_row = d_policy_sel.w + (bits * 4u + umulhi32(rnd.y, popc32(bits))) * kMoveSelRow;
+        } else {
+            action = load_action(a.actions, a.action_dtype, g);
+            sel_row = d_move_sel + (action & 3u) * kMoveSelRow;
+        }
+        uint32_t r0 = bd[j].x, r1 = bd[j].y, r2 = bd[j].z, r3 = bd[j].w;
+        Fusions f;
+        const uint32_t row_action = move_board_sel(r0, r1, r2, r3, sel_row, f);
+        if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
+            action = row_action;
+            if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
+        }
+        const bool moved = (action < 4u) && (((r0 ^ bd[j].x) | (r1 ^ bd[j].y) | (r2 ^ bd[j].z) | (r3 ^ bd[j].w)) != 0u);
+        if (moved) {
+            const uint32_t gain = fusion_gain(f);
+            float reward;
+            if (a.reward_kind == ML2048_REWARD_NORMAL) {
+                reward = (float)gain;
+            } else if (a.reward_kind == ML2048_REWARD_IMPROVED) {
+                const uint32_t s0 = r0 & 0xffu, p0 = bd[j].x & 0xffu;
+                const int extra = (s0 ? (64 << s0) : 0) - (p0 ? (64 << p0) : 0);
+                reward = (float)((int)gain + extra);
+            } else if (a.reward_kind == ML2048_REWARD_RANK) {
+                reward = (float)fusion_rank(f);
+            } else if (a.reward_kind == ML2048_REWARD_MAXCELL) {
+                const uint32_t cur = max_cell(r0, r1, r2, r3), old = max_cell(bd[j].x, bd[j].y, bd[j].z, bd[j].w);
+                reward = (float)f.count + ((cur > old) ? (float)(1u << cur) : 0.0f);
+            } else {
+                reward = (float)gain;
+            }
+            const float score = __int_as_float(ss[j].y) + (float)gain;
+            const int32_t nstep = ss[j].x + 1;
+            const uint32_t n0 = occupied_signs(r0), n1 = occupied_signs(r1), n2 = occupied_signs(r2), n3 = occupied_signs(r3);
+            uint32_t cell;
+            if (kRng == ML2048_RNG_REPLAY) {
+                const uint32_t row = ((uint32_t)rand_seed + (uint32_t)slot) & (uint32_t)(kRandRows - 1);
+                const uint4 keys = __ldg(reinterpret_cast<const uint4 *>(keys_table) + row);
+                cell = first_empty_key(keys.x, keys.y, keys.z, keys.w, n0, n1, n2, n3) & 15u;
+            } else {
+                const uint32_t empties = empties16(~n0 & kHi, ~n1 & kHi, ~n2 & kHi, ~n3 & kHi);
+                cell = kth_set_bit16(empties, umulhi32(rnd.x, popc32(empties)));
+            }
+            put_cell(r0, r1, r2, r3, cell, 2u - ((two_mask >> cell) & 1u));
+            const uint32_t vm = valid_mask(r0, r1, r2, r3);
+            const bool dead = vm == 0u;
+            valid_out[j] = vm;
+            reward_out[j] = reward;
+            step_score[j] = make_int2(nstep, __float_as_int(score));
+            terminated[j] = dead ? 1 : 0;
+            invalid[j] = 0;
+            if (dead && a.stats) {
+                ml2048_stats *st = a.stats + (blockIdx.x % ML2048_STATS_REPLICAS);
+                const unsigned long long sc = (unsigned long long)score;
+                atomicAdd(&st->max_tile_hist[min(max_cell(r0, r1, r2, r3), 19u)], 1ull);
+                atomicAdd(&st->episodes, 1ull);
+                atomicAdd(&st->score_sum, sc);
+                atomicAdd(&st->step_sum, (unsigned long long)nstep);
+                atomicMax(&st->score_max, sc);
+            }
+        } else {
+            r0 = bd[j].x, r1 = bd[j].y, r2 = bd[j].z, r3 = bd[j].w;
+            valid_out[j] = want_mask ? mask_now[j] : valid_mask(r0, r1, r2, r3);
+            invalid[j] = 1;
+        }
+        board_out[j] = make_uint4(r0, r1, r2, r3);
+    }
+}
+
 // ---- auto-reset (VecGame.prepare, game_numba.py:619-658) -----------------------------------
 // Pass 1: terminated games per tile of 4096 slots.  Pass 2: exclusive scan over tiles (one block),
 // advances the id counter.  Pass 3: per tile, slot-ordered offsets -> ids, reset indices, fresh boards.
@@ -1155,11 +1332,31 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
     return launch_status();
 }
 
+// ML2048_STEP=single in the environment keeps large lean batches on the one-game-per-thread kernel (A/B measurements and the
+// differential test of the two kernels); read once, or on every call when ML2048_PREPARE_RECHECK is set.
+inline bool force_single_step()
+{
+    static const bool recheck = getenv("ML2048_PREPARE_RECHECK") != nullptr;
+    static const bool single_at_start = [] { const char *m = getenv("ML2048_STEP"); return m && m[0] == 's'; }();
+    if (!recheck) return single_at_start;
+    const char *m = getenv("ML2048_STEP");
+    return m && m[0] == 's';
+}
+
 template <int kRng>
 int launch_step(const ml2048_step_args &a, cudaStream_t s)
 {
     const bool full = a.action_mode == ML2048_ACTIONS_FROM_LOGITS || a.episode_max_tile || a.traj_state || a.tr_state || a.tr_valid_actions ||
                       a.tr_action || a.tr_reward || a.tr_next_state || a.tr_next_valid_actions || a.tr_step || a.tr_terminated;
+    const int onehot_kind = a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE;
+    if (!full && !a.merged && onehot_kind == ML2048_ONEHOT_NONE && a.num_games >= kPairMinGames && !force_single_step()) {
+        // the lean core-only configuration at large batches: two games per thread
+        const unsigned grid = (unsigned)(((a.num_games + 1) / 2 + kPairThreads - 1) / kPairThreads);
+        clear_stale_error();
+        if (a.reset_rank) step_pair_kernel<kRng, true><<<grid, kPairThreads, 0, s>>>(a);
+        else step_pair_kernel<kRng, false><<<grid, kPairThreads, 0, s>>>(a);
+        return launch_status();
+    }
     if (a.reset_rank) {
         // the fused auto-reset is built for the lean kernels (the synthetic random-policy rollouts it serves)
         if (full) return ML2048_E_ENUM;
