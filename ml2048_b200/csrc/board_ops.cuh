@@ -73,11 +73,33 @@ ML2048_FN uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c)
 // The step kernel saturates the integer ALU pipe (LOP3/PRMT/SHF/IADD: 84 % busy in ncu) while the FMA pipe
 // idles (15 %).  An add written as `a * one + b` with a multiplier the compiler cannot see through is issued
 // as IMAD on the FMA pipe; `one` lives in constant memory (an IMAD operand can come straight from there).
+// The same goes for `a * 2^k + b` (a left shift, or a scaled add) and for `x & 0x01010101` of a full-byte mask x (bytes 0x00 /
+// 0xff): x = 255 * e with e the 0/1 bytes, and 255 is odd, so e = x * 255^-1 = x * 0xfefefeff (mod 2^32) -- one IMAD computes
+// `a + (x & 0x01010101)`.
 #if defined(__CUDACC__)
 __constant__ uint32_t c_opaque_one = 1u;
+__constant__ uint32_t c_opaque_two = 2u;
+__constant__ uint32_t c_opaque_256 = 256u;
+__constant__ uint32_t c_opaque_2p23 = 0x00800000u;
+__constant__ uint32_t c_opaque_inv255 = 0xfefefeffu;
 ML2048_FN uint32_t add_on_fma_pipe(uint32_t a, uint32_t b) { return a * c_opaque_one + b; }
+ML2048_FN uint32_t twice_plus_on_fma_pipe(uint32_t a, uint32_t b) { return a * c_opaque_two + b; }
+ML2048_FN uint32_t shl8_on_fma_pipe(uint32_t a) { return a * c_opaque_256; }
+ML2048_FN uint32_t shl23_on_fma_pipe(uint32_t a) { return a * c_opaque_2p23; }
+ML2048_FN uint32_t add_ones_of_mask_on_fma_pipe(uint32_t a, uint32_t mask) { return mask * c_opaque_inv255 + a; }
+ML2048_FN float bits_as_float(uint32_t x) { return __uint_as_float(x); }
 #else
 ML2048_FN uint32_t add_on_fma_pipe(uint32_t a, uint32_t b) { return a + b; }
+ML2048_FN uint32_t twice_plus_on_fma_pipe(uint32_t a, uint32_t b) { return a * 2u + b; }
+ML2048_FN uint32_t shl8_on_fma_pipe(uint32_t a) { return a << 8; }
+ML2048_FN uint32_t shl23_on_fma_pipe(uint32_t a) { return a << 23; }
+ML2048_FN uint32_t add_ones_of_mask_on_fma_pipe(uint32_t a, uint32_t mask) { return mask * 0xfefefeffu + a; }
+ML2048_FN float bits_as_float(uint32_t x)
+{
+    float f;
+    __builtin_memcpy(&f, &x, 4);
+    return f;
+}
 #endif
 
 constexpr uint32_t kHi = 0x80808080u;
@@ -93,15 +115,18 @@ ML2048_FN uint32_t occupied_flags(uint32_t row) { return occupied_signs(row) & k
 // 0xff in every byte of x that is non-zero (bytes of x must be <= 0x80)
 ML2048_FN uint32_t nonzero_mask(uint32_t x) { return prmt_sign(add_on_fma_pipe(x, kLo7), 0u, 0xba98); }
 
-// What one move fused: `first`/`second` hold the exponents of the consumed tiles, one byte per line
-// (0 = no fusion); a line fuses at most twice.  From them: the reference's reward_fn_normal
-// (game_numba.py:408-438), reward_fn_rank (:469-484), the merged.sum() of reward_fn_maxcell (:502)
-// and the `merged` array itself.
+// What one move fused: `first`/`second` hold, one byte per line, the exponent of the consumed tiles PLUS 127 (0 = no fusion;
+// a line fuses at most twice).  The bias makes a byte the exponent field of the float 2^k (bit 7 doubles as the "fused"
+// flag, the low five bits are k - 1), which is how fusion_gain sums the rewards on the FMA pipe.  From them: the
+// reference's reward_fn_normal (game_numba.py:408-438), reward_fn_rank (:469-484), the merged.sum() of reward_fn_maxcell
+// (:502) and the `merged` array itself.
 struct Fusions {
     uint32_t first;
     uint32_t second;
-    uint32_t count;  // number of fusions of the move (<= 8)
 };
+
+// number of fusions of the move (<= 8)
+ML2048_FN uint32_t fusion_count(const Fusions &f) { return popc32(f.first & kHi) + popc32(f.second & kHi); }
 
 // Four lines pushed toward A at once.  Same result per line as the reference's _push_row
 // (game_numba.py:48-90): stable compaction of the tiles, then equal neighbours fuse once, in order
@@ -123,35 +148,38 @@ ML2048_FN void push4(uint32_t &A, uint32_t &B, uint32_t &C, uint32_t &D, Fusions
     C = (C & m) | (D & ~m);
     D = D & m;
     // which neighbours fuse (full-byte masks): a/b first, then b/c unless b was used, then c/d unless c was used
-    const uint32_t eab = ~nonzero_mask(A ^ B) & nonzero_mask(A);
-    const uint32_t ebc = ~nonzero_mask(B ^ C) & nonzero_mask(B) & ~eab;
-    const uint32_t ecd = ~nonzero_mask(C ^ D) & nonzero_mask(C) & ~ebc;
-    f.first = (A & eab) | (B & ebc) | (C & ecd & ~eab);  // per line these three exclude each other
-    f.second = C & ecd & eab;
-    f.count = (popc32(eab | ebc) + popc32(ecd)) >> 3;
+    const uint32_t sA = add_on_fma_pipe(A, kLo7), sB = add_on_fma_pipe(B, kLo7), sC = add_on_fma_pipe(C, kLo7);  // cell + 127
+    const uint32_t eab = ~nonzero_mask(A ^ B) & prmt_sign(sA, 0u, 0xba98);
+    const uint32_t ebc = ~nonzero_mask(B ^ C) & prmt_sign(sB, 0u, 0xba98) & ~eab;
+    const uint32_t ecd = ~nonzero_mask(C ^ D) & prmt_sign(sC, 0u, 0xba98) & ~ebc;
+    f.first = (sA & eab) | (sB & ebc) | (sC & ecd & ~eab);  // per line these three exclude each other
+    f.second = sC & ecd & eab;
     const uint32_t both = eab & ecd;    // [a+1, c+1, 0, 0]
     const uint32_t shift = eab | ebc;   // position C receives D
-    const uint32_t nA = add_on_fma_pipe(A, eab & kOnes);
-    const uint32_t nB = add_on_fma_pipe((C & eab) | (B & ~eab), (ebc | both) & kOnes);
-    const uint32_t nC = (D & shift & ~both) | (add_on_fma_pipe(C, ecd & kOnes) & ~shift);
+    const uint32_t nA = add_ones_of_mask_on_fma_pipe(A, eab);
+    const uint32_t nB = add_ones_of_mask_on_fma_pipe((C & eab) | (B & ~eab), ebc | both);
+    const uint32_t nC = (D & shift & ~both) | (add_ones_of_mask_on_fma_pipe(C, ecd) & ~shift);
     const uint32_t nD = D & ~(shift | ecd);
     A = nA, B = nB, C = nC, D = nD;
 }
 
-// sum over the (up to 8) fusions of 2^(k+1): the reference's reward_fn_normal
-ML2048_FN uint32_t fusion_gain(const Fusions &f)
+// sum over the (up to 8) fusions of 2^(k+1): the reference's reward_fn_normal, as the float the reward and the score are
+// (exact: every term is a power of two <= 2^18 and the sum stays below 2^22).  A candidate byte v = k + 127 shifted into the
+// exponent field IS the float 2^k, and v = 0 is 0.0f: one byte extraction (ALU pipe) per candidate, the shift as a multiply
+// and the sum on the FMA pipe -- the integer version (eight variable shifts and their adds) cost 21 ALU-pipe instructions.
+ML2048_FN float fusion_gain(const Fusions &f)
 {
-    // 1<<k for all eight candidate bytes (k <= 17, so the low five bits of a byte are the whole exponent and the
-    // bits above it in the word are ignored by the wrapping shift); an empty candidate (k = 0) adds 1, removed afterwards
-    uint32_t s = one_shl_wrap(f.first) + one_shl_wrap(f.first >> 8) + one_shl_wrap(f.first >> 16) + one_shl_wrap(f.first >> 24);
-    s += one_shl_wrap(f.second) + one_shl_wrap(f.second >> 8) + one_shl_wrap(f.second >> 16) + one_shl_wrap(f.second >> 24);
-    return (s - 8u + f.count) << 1;
+    float s = bits_as_float(shl23_on_fma_pipe(f.first & 0xffu)) + bits_as_float(shl23_on_fma_pipe(f.second & 0xffu));
+    s += bits_as_float(shl23_on_fma_pipe(prmt(f.first, 0u, 0x4441))) + bits_as_float(shl23_on_fma_pipe(prmt(f.second, 0u, 0x4441)));
+    s += bits_as_float(shl23_on_fma_pipe(prmt(f.first, 0u, 0x4442))) + bits_as_float(shl23_on_fma_pipe(prmt(f.second, 0u, 0x4442)));
+    s += bits_as_float(shl23_on_fma_pipe(prmt(f.first, 0u, 0x4443))) + bits_as_float(shl23_on_fma_pipe(prmt(f.second, 0u, 0x4443)));
+    return s + s;
 }
 
-// sum over the fusions of (k+1): reward_fn_rank
+// sum over the fusions of (k+1): reward_fn_rank.  (v & 31) = k - 1 for a fused candidate, 0 otherwise.
 ML2048_FN uint32_t fusion_rank(const Fusions &f)
 {
-    return (((f.first + f.second) * kOnes) >> 24) + f.count;
+    return ((((f.first & 0x1f1f1f1fu) + (f.second & 0x1f1f1f1fu)) * kOnes) >> 24) + 2u * fusion_count(f);
 }
 
 // the reference's `merged` u8[16] as four words: merged[k] = number of fusions that consumed exponent k.
@@ -164,8 +192,9 @@ ML2048_FN void fusion_log(const Fusions &f, uint32_t &m0, uint32_t &m1, uint32_t
     for (int i = 0; i < 2; ++i) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t k = (w[i] >> (8 * j)) & 0xffu;
-            if (k != 0u && k < 16u) nib += 1ull << (4u * k);
+            const uint32_t v = (w[i] >> (8 * j)) & 0xffu;
+            const uint32_t k = (v & 0x1fu) + 1u;
+            if (v != 0u && k < 16u) nib += 1ull << (4u * k);
         }
     }
     const uint32_t lo = (uint32_t)nib, hi = (uint32_t)(nib >> 32);
@@ -271,37 +300,63 @@ ML2048_FN void move_board(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3
 //   fuse on an axis      <=>  some tile equals its neighbour on that axis
 ML2048_FN uint32_t valid_mask(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
 {
-    const uint32_t n0 = occupied_flags(r0), n1 = occupied_flags(r1), n2 = occupied_flags(r2), n3 = occupied_flags(r3);
-    // slides on the 16-bit occupancy mask (bit 4*row+col; the gathers are multiplies, i.e. FMA-pipe work):
-    // a tile at col j+1 next to an empty col j can slide left, and so on
-    const uint32_t m = 0x00204081u;  // gathers bits 7,15,23,31 of a flag word into the top nibble
-    const uint32_t occ = ((n0 * m) >> 28) | (((n1 * m) >> 24) & 0xf0u) | (((n2 * m) >> 20) & 0xf00u) | (((n3 * m) >> 16) & 0xf000u);
-    const uint32_t emp = ~occ;
-    const bool left = ((occ >> 1) & emp & 0x7777u) != 0u;
-    const bool right = ((occ << 1) & emp & 0xeeeeu) != 0u;
-    const bool up = ((occ >> 4) & emp & 0x0fffu) != 0u;
-    const bool down = ((occ << 4) & emp & 0xfff0u) != 0u;
+    const uint32_t s0 = occupied_signs(r0), s1 = occupied_signs(r1), s2 = occupied_signs(r2), s3 = occupied_signs(r3);
+    // Slides on ONE packed word P: byte j = column j, bit 7-i of it = "row i holds a tile".  Each row's flag is born at its own
+    // bit position by a scaled add (cells are <= 17): c + 0x7f sets bit 7, 2c + 0x3e bit 6, c + 0x1f bit 5 exactly when c >= 1;
+    // for bit 4, c + 0x0f covers 1..16 and the cell's own bit 4 covers 16 and 17.  The adds are FMA-pipe work; three LOP3 merge them.
+    const uint32_t x1 = twice_plus_on_fma_pipe(r1, 0x3e3e3e3eu), x2 = add_on_fma_pipe(r2, 0x1f1f1f1fu), x3 = add_on_fma_pipe(r3, 0x0f0f0f0fu);
+    const uint32_t t3 = (x3 | r3) & 0x10101010u;
+    const uint32_t P = (s0 & kHi) | (x1 & 0x40404040u) | (x2 & 0x20202020u) | t3;
+    const uint32_t Pr = P >> 8;                    // byte j = column j + 1
+    const uint32_t Pl = shl8_on_fma_pipe(P);       // byte j = column j - 1
+    const uint32_t Pd = twice_plus_on_fma_pipe(P, 0u);  // bit 7-i = row i + 1 (bit 0 of a byte catches the neighbour's bit 7: masked below)
     // fusions: xor of neighbours is zero where the first one is a tile (byte 3 of a row xor is the cell itself)
-    const uint32_t hfuse = (~add_on_fma_pipe(r0 ^ (r0 >> 8), kLo7) & n0) | (~add_on_fma_pipe(r1 ^ (r1 >> 8), kLo7) & n1) |
-                           (~add_on_fma_pipe(r2 ^ (r2 >> 8), kLo7) & n2) | (~add_on_fma_pipe(r3 ^ (r3 >> 8), kLo7) & n3);
-    const uint32_t vfuse = (~add_on_fma_pipe(r0 ^ r1, kLo7) & n0) | (~add_on_fma_pipe(r1 ^ r2, kLo7) & n1) |
-                           (~add_on_fma_pipe(r2 ^ r3, kLo7) & n2);
-    const bool hf = (hfuse & kHi) != 0u, vf = (vfuse & kHi) != 0u;
-    const uint32_t l = left || hf, r = right || hf, u = up || vf, d = down || vf;
+    const uint32_t hfuse = ((~add_on_fma_pipe(r0 ^ (r0 >> 8), kLo7) & s0) | (~add_on_fma_pipe(r1 ^ (r1 >> 8), kLo7) & s1) |
+                            (~add_on_fma_pipe(r2 ^ (r2 >> 8), kLo7) & s2) | (~add_on_fma_pipe(r3 ^ (r3 >> 8), kLo7) & s3)) & kHi;
+    const uint32_t vfuse = (~add_on_fma_pipe(r0 ^ r1, kLo7) & s0) | (~add_on_fma_pipe(r1 ^ r2, kLo7) & s1) |
+                           (~add_on_fma_pipe(r2 ^ r3, kLo7) & s2);
+    const bool vf = (vfuse & kHi) != 0u;
+    // a tile at column j+1 next to an empty column j can slide left, and so on
+    const uint32_t l = (((Pr & ~P) | hfuse) != 0u) ? 1u : 0u;
+    const uint32_t r = (((Pl & ~P) | hfuse) != 0u) ? 1u : 0u;
+    const uint32_t u = (((Pd & ~P & 0xe0e0e0e0u) != 0u) || vf) ? 1u : 0u;
+    const uint32_t d = (((P & ~Pd & 0xe0e0e0e0u) != 0u) || vf) ? 1u : 0u;
     return (l + r * 0x100u) + (u * 0x10000u + d * 0x1000000u);  // disjoint bytes: adds (IMAD) instead of shifts + ORs
 }
 
-// Write `value` into cell `cell` (0..15) of the (empty there) board: one 64-bit shift places it inside its half of
-// the board, one predicate picks the half.
+// Write `value` (a tile exponent, or any small multiplier) into cell `cell` (0..15) of the (empty there) board.  The sixteen
+// boards with a single 1 live in a 256-byte table (L1-resident): one vector load and four multiply-adds on the FMA pipe
+// instead of a 64-bit shift and four selects (14 ALU-pipe instructions with the 2-or-4 decision; 4 now).
+struct CellTable {
+    uint32_t w[16 * 4];
+};
+
+constexpr CellTable make_cell_table()
+{
+    CellTable t{};
+    for (uint32_t c = 0; c < 16; ++c) t.w[4 * c + (c >> 2)] = 1u << (8u * (c & 3u));
+    return t;
+}
+
+#if defined(__CUDACC__)
+__device__ const CellTable d_cell_one = make_cell_table();
+#endif
+
 ML2048_FN void put_cell(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t cell, uint32_t value)
 {
-    const unsigned long long v = (unsigned long long)value << ((cell & 7u) * 8u);
-    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-    const bool top = (cell & 8u) != 0u;
-    r0 |= top ? 0u : lo;
-    r1 |= top ? 0u : hi;
-    r2 |= top ? lo : 0u;
-    r3 |= top ? hi : 0u;
+#if defined(__CUDACC__)
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(d_cell_one.w) + cell);
+    r0 = t.x * value + r0;
+    r1 = t.y * value + r1;
+    r2 = t.z * value + r2;
+    r3 = t.w * value + r3;
+#else
+    constexpr CellTable tab = make_cell_table();
+    r0 += tab.w[4 * cell] * value;
+    r1 += tab.w[4 * cell + 1] * value;
+    r2 += tab.w[4 * cell + 2] * value;
+    r3 += tab.w[4 * cell + 3] * value;
+#endif
 }
 
 // Replay-mode spawn position.  The reference walks row `p` of randperm and takes the first entry whose
@@ -440,7 +495,7 @@ constexpr FreshTable make_fresh_table()
         const uint32_t c0 = idx >> 6, c1 = (idx >> 2) & 15u, t0 = (idx >> 1) & 1u, t1 = idx & 1u;
         uint8_t b[16] = {};
         b[c0] = (uint8_t)(2u - t0);
-        b[c1] = (uint8_t)(b[c1] | (2u - t1));  // c0 == c1 cannot occur (distinct cells); OR like the kernel's put_cell
+        b[c1] = (uint8_t)(b[c1] + (2u - t1));  // c0 == c1 cannot occur (distinct cells); an add like the kernel's put_cell
         for (int row = 0; row < 4; ++row)
             t.board[4 * idx + row] = (uint32_t)b[4 * row] | ((uint32_t)b[4 * row + 1] << 8) | ((uint32_t)b[4 * row + 2] << 16) |
                                      ((uint32_t)b[4 * row + 3] << 24);

@@ -419,28 +419,28 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
 
         if (moved) {
             // reward_fn (:728) and the score increment (:729-731)
-            const uint32_t gain = fusion_gain(f);
+            const float gain = fusion_gain(f);  // an exact integer < 2^22
             float reward;
             if (a.reward_kind == ML2048_REWARD_NORMAL) {
-                reward = (float)gain;
+                reward = gain;
             } else if (a.reward_kind == ML2048_REWARD_IMPROVED) {
-                // potential shaping on cell 0, game_numba.py:455-466 (all terms are exact integers in f32)
+                // potential shaping on cell 0, game_numba.py:455-466 (all terms are exact integers in f32: |extra| <= 2^23)
                 const uint32_t s0 = r0 & 0xffu, p0 = bd.x & 0xffu;
                 const int extra = (s0 ? (64 << s0) : 0) - (p0 ? (64 << p0) : 0);
-                reward = (float)((int)gain + extra);
+                reward = gain + (float)extra;
             } else if (a.reward_kind == ML2048_REWARD_RANK) {
                 reward = (float)fusion_rank(f);
             } else if (a.reward_kind == ML2048_REWARD_MAXCELL) {
                 const uint32_t cur = max_cell(r0, r1, r2, r3), old = max_cell(bd.x, bd.y, bd.z, bd.w);
-                reward = (float)f.count + ((cur > old) ? (float)(1u << cur) : 0.0f);
+                reward = (float)fusion_count(f) + ((cur > old) ? (float)(1u << cur) : 0.0f);
             } else {
-                reward = (float)gain;
+                reward = gain;
             }
                         // step count and score are the halves of ONE 8-byte record per game: one load, one store, one stream
             int2 *const step_score = reinterpret_cast<int2 *>(a.step) + g;
             // a game reset by this very launch starts from step 0, score 0 (its record still holds the finished game's)
             const int2 old_ss = (kReset && was_reset) ? make_int2(0, 0) : *step_score;
-            const float score = __int_as_float(old_ss.y) + (float)gain;
+            const float score = __int_as_float(old_ss.y) + gain;
             const int32_t nstep = old_ss.x + 1;
 
             // spawn one tile (_spawn2 with count = 1, game_numba.py:733)
@@ -682,25 +682,29 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
             action = row_action;
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
         }
-        const bool moved = (action < 4u) && (((r0 ^ bd[j].x) | (r1 ^ bd[j].y) | (r2 ^ bd[j].z) | (r3 ^ bd[j].w)) != 0u);
+        // valid_actions[action] (game_numba.py:718) == "the move changes the board".  The random policy only ever picks a valid
+        // direction, so there the move counts exactly when the game has one (mask != 0): no comparison of the boards
+        const bool moved = a.action_mode == ML2048_ACTIONS_RANDOM_VALID
+                               ? mask_now[j] != 0u
+                               : (action < 4u) && (((r0 ^ bd[j].x) | (r1 ^ bd[j].y) | (r2 ^ bd[j].z) | (r3 ^ bd[j].w)) != 0u);
         if (moved) {
-            const uint32_t gain = fusion_gain(f);
+            const float gain = fusion_gain(f);
             float reward;
             if (a.reward_kind == ML2048_REWARD_NORMAL) {
-                reward = (float)gain;
+                reward = gain;
             } else if (a.reward_kind == ML2048_REWARD_IMPROVED) {
                 const uint32_t s0 = r0 & 0xffu, p0 = bd[j].x & 0xffu;
                 const int extra = (s0 ? (64 << s0) : 0) - (p0 ? (64 << p0) : 0);
-                reward = (float)((int)gain + extra);
+                reward = gain + (float)extra;
             } else if (a.reward_kind == ML2048_REWARD_RANK) {
                 reward = (float)fusion_rank(f);
             } else if (a.reward_kind == ML2048_REWARD_MAXCELL) {
                 const uint32_t cur = max_cell(r0, r1, r2, r3), old = max_cell(bd[j].x, bd[j].y, bd[j].z, bd[j].w);
-                reward = (float)f.count + ((cur > old) ? (float)(1u << cur) : 0.0f);
+                reward = (float)fusion_count(f) + ((cur > old) ? (float)(1u << cur) : 0.0f);
             } else {
-                reward = (float)gain;
+                reward = gain;
             }
-            const float score = __int_as_float(ss[j].y) + (float)gain;
+            const float score = __int_as_float(ss[j].y) + gain;
             const int32_t nstep = ss[j].x + 1;
             const uint32_t n0 = occupied_signs(r0), n1 = occupied_signs(r1), n2 = occupied_signs(r2), n3 = occupied_signs(r3);
             uint32_t cell;

@@ -18,9 +18,9 @@ void hs_move(const uint8_t *board16, int action, uint8_t *out16, uint32_t *gain,
     Fusions f;
     move_board(r[0], r[1], r[2], r[3], (uint32_t)action, f);
     memcpy(out16, r, 16);
-    *gain = fusion_gain(f);
+    *gain = (uint32_t)fusion_gain(f);
     *rank = fusion_rank(f);
-    *count = f.count;
+    *count = fusion_count(f);
     uint32_t m[4];
     fusion_log(f, m[0], m[1], m[2], m[3]);
     memcpy(merged16, m, 16);

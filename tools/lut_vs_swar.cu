@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) move_swar(const uint4 *boards, const uint
     Fusions f;
     move_board_sel(r0, r1, r2, r3, d_move_sel + (actions[g] & 3u) * kMoveSelRow, f);
     out[g] = make_uint4(r0, r1, r2, r3);
-    gain[g] = fusion_gain(f);
+    gain[g] = (uint32_t)fusion_gain(f);
 }
 
 __device__ __forceinline__ uint32_t pack_line(uint32_t w)  // four bytes < 16 -> four nibbles
@@ -98,13 +98,14 @@ __global__ void __launch_bounds__(1024, 1) move_lut(const uint4 *boards, const u
         // consumed exponents, two nibbles per line, as one word: byte i = line i
         const uint32_t fz = (uint32_t)s_fuse[i0] | ((uint32_t)s_fuse[i1] << 8) | ((uint32_t)s_fuse[i2] << 16) | ((uint32_t)s_fuse[i3] << 24);
         Fusions f;
-        f.first = fz & 0x0f0f0f0fu;
-        f.second = (fz >> 4) & 0x0f0f0f0fu;
-        f.count = popc32(nonzero_mask(f.first) & kOnes) + popc32(nonzero_mask(f.second) & kOnes);
+        // Fusions holds exponent + 127 per fused candidate (board_ops.cuh)
+        const uint32_t e1 = fz & 0x0f0f0f0fu, e2 = (fz >> 4) & 0x0f0f0f0fu;
+        f.first = (e1 + kLo7) & nonzero_mask(e1);
+        f.second = (e2 + kLo7) & nonzero_mask(e2);
         const uint32_t u0 = prmt_sign(L0, L2, sb.x), u1 = prmt_sign(L1, L3, sb.x);
         const uint32_t u2 = prmt_sign(L0, L2, sb.y), u3 = prmt_sign(L1, L3, sb.y);
         out[g] = make_uint4(prmt_sign(u0, u1, sb.z), prmt_sign(u0, u1, sb.w), prmt_sign(u2, u3, sb.z), prmt_sign(u2, u3, sb.w));
-        gain[g] = fusion_gain(f);
+        gain[g] = (uint32_t)fusion_gain(f);
     }
 }
 
