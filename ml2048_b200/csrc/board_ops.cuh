@@ -82,11 +82,19 @@ __constant__ uint32_t c_opaque_two = 2u;
 __constant__ uint32_t c_opaque_256 = 256u;
 __constant__ uint32_t c_opaque_2p23 = 0x00800000u;
 __constant__ uint32_t c_opaque_inv255 = 0xfefefeffu;
-ML2048_FN uint32_t add_on_fma_pipe(uint32_t a, uint32_t b) { return a * c_opaque_one + b; }
-ML2048_FN uint32_t twice_plus_on_fma_pipe(uint32_t a, uint32_t b) { return a * c_opaque_two + b; }
-ML2048_FN uint32_t shl8_on_fma_pipe(uint32_t a) { return a * c_opaque_256; }
-ML2048_FN uint32_t shl23_on_fma_pipe(uint32_t a) { return a * c_opaque_2p23; }
-ML2048_FN uint32_t add_ones_of_mask_on_fma_pipe(uint32_t a, uint32_t mask) { return mask * c_opaque_inv255 + a; }
+// The multiply-add is written as PTX so that the front end cannot rewrite around it: it turned `~(a * one + b)` into
+// `(-a) * one + ~b`, a negation (one more instruction) where the NOT would have been free inside the LOP3 that consumes it.
+ML2048_FN uint32_t mad_opaque(uint32_t a, uint32_t m, uint32_t b)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(b));
+    return d;
+}
+ML2048_FN uint32_t add_on_fma_pipe(uint32_t a, uint32_t b) { return mad_opaque(a, c_opaque_one, b); }
+ML2048_FN uint32_t twice_plus_on_fma_pipe(uint32_t a, uint32_t b) { return mad_opaque(a, c_opaque_two, b); }
+ML2048_FN uint32_t shl8_on_fma_pipe(uint32_t a) { return mad_opaque(a, c_opaque_256, 0u); }
+ML2048_FN uint32_t shl23_on_fma_pipe(uint32_t a) { return mad_opaque(a, c_opaque_2p23, 0u); }
+ML2048_FN uint32_t add_ones_of_mask_on_fma_pipe(uint32_t a, uint32_t mask) { return mad_opaque(mask, c_opaque_inv255, a); }
 ML2048_FN float bits_as_float(uint32_t x) { return __uint_as_float(x); }
 #else
 ML2048_FN uint32_t add_on_fma_pipe(uint32_t a, uint32_t b) { return a + b; }

@@ -581,7 +581,10 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
 constexpr int kPairThreads = ML2048_PAIR_THREADS;
 constexpr int64_t kPairMinGames = 1 << 17;  // below this the batch is latency-bound: more, smaller threads win
 
-template <int kRng, bool kReset>
+// kRandom: the in-kernel random-valid policy (else caller-given actions); kNormalReward: reward_fn_normal (else the
+// reward kind is looked up at run time) -- compile-time switches for what is uniform over a launch, each worth a handful of
+// issue slots per game (parameter load, compare, branch).
+template <int kRng, bool kReset, bool kRandom, bool kNormalReward>
 __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pair_kernel(const ml2048_step_args a)
 {
     const int64_t g0 = ((int64_t)blockIdx.x * kPairThreads + threadIdx.x) * 2;  // this thread owns games g0 and g0 + 1
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
     uint4 bd[2];
     bd[0] = board_in[0];
     bd[1] = live1 ? board_in[1] : make_uint4(0, 0, 0, 0);
-    const bool want_mask = kReset || a.action_mode != ML2048_ACTIONS_GIVEN;
+    const bool want_mask = kReset || kRandom;
     uint32_t mask_now[2] = {1u, 1u};
     if (want_mask) {
         const uint32_t *valid_in = reinterpret_cast<const uint32_t *>(a.valid_in) + g0;
@@ -665,10 +668,10 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
         const int64_t g = g0 + j;
         const uint64_t slot = (uint64_t)(a.slot_base + g);
         u32x2 rnd = {0u, 0u};
-        if (kRng == ML2048_RNG_PHILOX || a.action_mode != ML2048_ACTIONS_GIVEN) rnd = slot_draws(slot, philox_counter, a.philox_seed, 0u);
+        if (kRng == ML2048_RNG_PHILOX || kRandom) rnd = slot_draws(slot, philox_counter, a.philox_seed, 0u);
         uint32_t action = 0u;
         const uint32_t *sel_row;
-        if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
+        if (kRandom) {
             const uint32_t bits = mask_bits4(mask_now[j]);
             sel_row = d_policy_sel.w + (bits * 4u + umulhi32(rnd.y, popc32(bits))) * kMoveSelRow;
         } else {
@@ -678,19 +681,19 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
         uint32_t r0 = bd[j].x, r1 = bd[j].y, r2 = bd[j].z, r3 = bd[j].w;
         Fusions f;
         const uint32_t row_action = move_board_sel(r0, r1, r2, r3, sel_row, f);
-        if (a.action_mode == ML2048_ACTIONS_RANDOM_VALID) {
+        if (kRandom) {
             action = row_action;
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
         }
         // valid_actions[action] (game_numba.py:718) == "the move changes the board".  The random policy only ever picks a valid
         // direction, so there the move counts exactly when the game has one (mask != 0): no comparison of the boards
-        const bool moved = a.action_mode == ML2048_ACTIONS_RANDOM_VALID
+        const bool moved = kRandom
                                ? mask_now[j] != 0u
                                : (action < 4u) && (((r0 ^ bd[j].x) | (r1 ^ bd[j].y) | (r2 ^ bd[j].z) | (r3 ^ bd[j].w)) != 0u);
         if (moved) {
             const float gain = fusion_gain(f);
             float reward;
-            if (a.reward_kind == ML2048_REWARD_NORMAL) {
+            if (kNormalReward || a.reward_kind == ML2048_REWARD_NORMAL) {
                 reward = gain;
             } else if (a.reward_kind == ML2048_REWARD_IMPROVED) {
                 const uint32_t s0 = r0 & 0xffu, p0 = bd[j].x & 0xffu;
@@ -1357,8 +1360,18 @@ int launch_step(const ml2048_step_args &a, cudaStream_t s)
         // the lean core-only configuration at large batches: two games per thread
         const unsigned grid = (unsigned)(((a.num_games + 1) / 2 + kPairThreads - 1) / kPairThreads);
         clear_stale_error();
-        if (a.reset_rank) step_pair_kernel<kRng, true><<<grid, kPairThreads, 0, s>>>(a);
-        else step_pair_kernel<kRng, false><<<grid, kPairThreads, 0, s>>>(a);
+        const bool normal = a.reward_kind == ML2048_REWARD_NORMAL;
+        const bool random = a.action_mode == ML2048_ACTIONS_RANDOM_VALID;
+        if (a.reset_rank) {  // the fused auto-reset implies the random policy (checked by ml2048_step)
+            if (normal) step_pair_kernel<kRng, true, true, true><<<grid, kPairThreads, 0, s>>>(a);
+            else step_pair_kernel<kRng, true, true, false><<<grid, kPairThreads, 0, s>>>(a);
+        } else if (random) {
+            if (normal) step_pair_kernel<kRng, false, true, true><<<grid, kPairThreads, 0, s>>>(a);
+            else step_pair_kernel<kRng, false, true, false><<<grid, kPairThreads, 0, s>>>(a);
+        } else {
+            if (normal) step_pair_kernel<kRng, false, false, true><<<grid, kPairThreads, 0, s>>>(a);
+            else step_pair_kernel<kRng, false, false, false><<<grid, kPairThreads, 0, s>>>(a);
+        }
         return launch_status();
     }
     if (a.reset_rank) {
