@@ -532,18 +532,29 @@ ML2048_FN u32x2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k)
     return u32x2{c0, c1};
 }
 
-// The two uniform words of global slot `slot` at counter `counter` of stream `tag` (0 = step, kResetStream = auto-reset):
-// Philox counter = (slot low word, counter low word ^ high words * odd constants); key = seed ^ tag.  The key depends on
-// nothing but the seed (a kernel parameter), so its ten round values are computed once per warp on the uniform datapath --
-// the step counter may come from a device-resident schedule entry, i.e. from a vector register, and a key built from it
-// costs nine ALU adds per game-step.
+// One Philox2x32-10 block of stream `tag` (0 = the policy's words, kSpawnStream = the spawn cells of Philox mode, kResetStream
+// = the auto-reset's two cells): counter = (index low word, counter low word ^ high words * odd constants), key = seed ^ tag.
+// The key depends on nothing but the seed (a kernel parameter), so its ten round values are computed once per warp on the
+// uniform datapath -- the step counter may come from a device-resident schedule entry, i.e. from a vector register, and a key
+// built from it costs nine ALU adds per game-step.
 constexpr uint32_t kResetStream = 0x80000000u;
+constexpr uint32_t kSpawnStream = 0x40000000u;
 
-ML2048_FN u32x2 slot_draws(uint64_t slot, uint64_t counter, uint64_t seed, uint32_t tag)
+ML2048_FN u32x2 slot_draws(uint64_t index, uint64_t counter, uint64_t seed, uint32_t tag)
 {
     const uint32_t key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ tag;
-    const uint32_t c1 = (uint32_t)counter ^ ((uint32_t)(counter >> 32) * 0x85EBCA6Bu) ^ ((uint32_t)(slot >> 32) * 0xC2B2AE35u);
-    return philox2x32_10((uint32_t)slot, c1, key);
+    const uint32_t c1 = (uint32_t)counter ^ ((uint32_t)(counter >> 32) * 0x85EBCA6Bu) ^ ((uint32_t)(index >> 32) * 0xC2B2AE35u);
+    return philox2x32_10((uint32_t)index, c1, key);
+}
+
+// The ONE uniform word a game-step takes from the policy stream (and, in Philox mode, from the spawn stream): a block holds
+// two words, so it serves a PAIR of global slots -- block index = slot >> 1, the even slot takes .x, the odd one .y.  A thread
+// that owns both slots of a pair (step_pair_kernel) computes the block once; draws stay a function of (seed, global slot,
+// counter) alone, i.e. independent of batch size, sharding and kernel variant.
+ML2048_FN uint32_t slot_word(uint64_t slot, uint64_t counter, uint64_t seed, uint32_t tag)
+{
+    const u32x2 b = slot_draws(slot >> 1, counter, seed, tag);
+    return (slot & 1ull) ? b.y : b.x;
 }
 
 // Masked categorical sample (policy/actor_critic.py:56-76): invalid actions get finfo.min, the logits are

@@ -370,9 +370,11 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
 
     if (live) {
         const uint64_t slot = (uint64_t)(a.slot_base + g);
-        // one Philox2x32-10 block per game-step: .x picks the spawn cell (Philox mode), .y is the policy's uniform word
-        u32x2 rnd = {0u, 0u};
-        if (kRng == ML2048_RNG_PHILOX || a.action_mode != ML2048_ACTIONS_GIVEN) rnd = slot_draws(slot, philox_counter, a.philox_seed, 0u);
+        // one uniform word per game-step from the policy stream and (Philox mode) one from the spawn stream; a Philox2x32-10
+        // block serves the two slots of a pair (board_ops.cuh: slot_word)
+        u32x2 rnd = {0u, 0u};  // .x picks the spawn cell (Philox mode), .y is the policy's uniform word
+        if (kRng == ML2048_RNG_PHILOX) rnd.x = slot_word(slot, philox_counter, a.philox_seed, kSpawnStream);
+        if (a.action_mode != ML2048_ACTIONS_GIVEN) rnd.y = slot_word(slot, philox_counter, a.philox_seed, 0u);
         uint32_t action;
         const auto current_mask = [&]() -> uint32_t { return mask_now; };
         const uint32_t *sel_row;  // the move's permute selectors (board_ops.cuh)
@@ -662,13 +664,35 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
         }
     }
 
+    // the uniform words of the two games: one Philox block per stream serves both when the thread's first global slot is
+    // even (always, unless a shard starts at an odd slot)
+    const uint64_t slot0 = (uint64_t)(a.slot_base + g0);
+    uint32_t policy_word[2] = {0u, 0u}, spawn_word[2] = {0u, 0u};
+    if (kRandom) {
+        if ((a.slot_base & 1) == 0) {
+            const u32x2 b = slot_draws(slot0 >> 1, philox_counter, a.philox_seed, 0u);
+            policy_word[0] = b.x, policy_word[1] = b.y;
+        } else {
+            policy_word[0] = slot_word(slot0, philox_counter, a.philox_seed, 0u);
+            policy_word[1] = slot_word(slot0 + 1, philox_counter, a.philox_seed, 0u);
+        }
+    }
+    if (kRng == ML2048_RNG_PHILOX) {
+        if ((a.slot_base & 1) == 0) {
+            const u32x2 b = slot_draws(slot0 >> 1, philox_counter, a.philox_seed, kSpawnStream);
+            spawn_word[0] = b.x, spawn_word[1] = b.y;
+        } else {
+            spawn_word[0] = slot_word(slot0, philox_counter, a.philox_seed, kSpawnStream);
+            spawn_word[1] = slot_word(slot0 + 1, philox_counter, a.philox_seed, kSpawnStream);
+        }
+    }
+
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         if (j == 1 && !live1) break;
         const int64_t g = g0 + j;
-        const uint64_t slot = (uint64_t)(a.slot_base + g);
-        u32x2 rnd = {0u, 0u};
-        if (kRng == ML2048_RNG_PHILOX || kRandom) rnd = slot_draws(slot, philox_counter, a.philox_seed, 0u);
+        const uint64_t slot = slot0 + j;
+        const u32x2 rnd = {spawn_word[j], policy_word[j]};
         uint32_t action = 0u;
         const uint32_t *sel_row;
         if (kRandom) {
@@ -1185,10 +1209,10 @@ __global__ void __launch_bounds__(kStepThreads) sample_random_valid_kernel(const
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= num_games) return;
     const uint64_t slot = (uint64_t)(slot_base + g);
-    const u32x2 rnd = slot_draws(slot, counter, seed, 0u);  // the same policy word the step kernel draws
+    const uint32_t word = slot_word(slot, counter, seed, 0u);  // the same policy word the step kernel draws
     const uint32_t bits = mask_bits4(valid[g]);
     const uint32_t nv = popc32(bits);
-    actions[g] = (uint8_t)(nv ? kth_valid_action(bits, umulhi32(rnd.y, nv)) : 0u);
+    actions[g] = (uint8_t)(nv ? kth_valid_action(bits, umulhi32(word, nv)) : 0u);
 }
 
 __global__ void __launch_bounds__(kStepThreads) sample_categorical_kernel(const float4 *logits, const uint32_t *valid, uint8_t *act8,
@@ -1198,12 +1222,12 @@ __global__ void __launch_bounds__(kStepThreads) sample_categorical_kernel(const 
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= num_games) return;
     const uint64_t slot = (uint64_t)(slot_base + g);
-    const u32x2 rnd = slot_draws(slot, counter, seed, 0u);  // the same policy word the step kernel draws
+    const uint32_t word = slot_word(slot, counter, seed, 0u);  // the same policy word the step kernel draws
     const uint32_t vm = valid[g];
     const uint32_t bits = ((vm & 0xffu) ? 1u : 0u) | ((vm & 0xff00u) ? 2u : 0u) | ((vm & 0xff0000u) ? 4u : 0u) | ((vm & 0xff000000u) ? 8u : 0u);
     const float4 lg = logits[g];
     float lp;
-    const uint32_t action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, rnd.y, lp);
+    const uint32_t action = sample_masked_categorical(lg.x, lg.y, lg.z, lg.w, bits, word, lp);
     if (act8) act8[g] = (uint8_t)action;
     if (act64) act64[g] = (long long)action;
     if (log_prob) log_prob[g] = lp;

@@ -104,6 +104,8 @@ void hs_philox2(const uint32_t *ctr2, uint32_t key, uint32_t *out2)
     out2[0] = o.x, out2[1] = o.y;
 }
 
+uint32_t hs_slot_word(uint64_t slot, uint64_t counter, uint64_t seed, uint32_t tag) { return slot_word(slot, counter, seed, tag); }
+
 void hs_slot_draws(uint64_t slot, uint64_t counter, uint64_t seed, uint32_t tag, uint32_t *out2)
 {
     const u32x2 o = slot_draws(slot, counter, seed, tag);

@@ -260,6 +260,18 @@ def test_slot_draws_key_schedule(shim):
     assert len(seen) == 7  # high words and the stream tag all matter
 
 
+def test_slot_word_serves_slot_pairs(shim):
+    """slot_word: the policy / spawn word of a global slot is one half of the Philox block of its slot PAIR (index = slot >> 1;
+    even slot -> .x, odd slot -> .y), for every stream tag."""
+    shim.hs_slot_word.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
+    shim.hs_slot_word.restype = ctypes.c_uint32
+    out = np.zeros(2, np.uint32)
+    for slot in (0, 1, 2, 3, 1000, 1001, (1 << 33) + 4, (1 << 33) + 5, 2**40 - 1):
+        for counter, seed, tag in ((0, 0, 0), (77, 123, 0), (77, 123, 0x40000000), ((3 << 32) + 1, (9 << 32) + 4, 0)):
+            shim.hs_slot_draws(slot >> 1, counter, seed, tag, out.ctypes.data)
+            assert shim.hs_slot_word(slot, counter, seed, tag) == int(out[slot & 1])
+
+
 def test_hypothesis_boards_against_oracle(shim, oracle):
     """Property-based: arbitrary boards (exponents 0..17, any density) x any direction: the product's SWAR move, mask,
     max tile and fusion bookkeeping equal the oracle's scalar restatement of the reference."""

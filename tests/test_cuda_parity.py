@@ -699,9 +699,10 @@ def test_single_launch_prepare_equals_three_launch_prepare(ml, m, onehot, monkey
 
 
 def test_device_draws_equal_host_philox2x32(ml):
-    """The kernels' per-game draw (slot_draws: Philox2x32-10 of (global slot, counter), key from the seed) against the
-    library's HOST Philox (known-answer tested on the CPU): with all four directions valid the random-valid sampler
-    returns floor(word * 4 / 2^32) of the policy word -- compared for slots and counters beyond 2^32 too."""
+    """The kernels' per-game draw (slot_word: one half of the Philox2x32-10 block of (global slot >> 1, counter), key from the
+    seed; even slot -> .x, odd slot -> .y) against the library's HOST Philox (known-answer tested on the CPU): with all four
+    directions valid the random-valid sampler returns floor(word * 4 / 2^32) of the policy word -- compared for slots and
+    counters beyond 2^32 too."""
     from ml2048_b200 import _lib
 
     lib = _lib.load()
@@ -709,7 +710,7 @@ def test_device_draws_equal_host_philox2x32(ml):
     valid = torch.ones((m, 4), dtype=torch.uint8, device="cuda")
     acts = torch.empty((m,), dtype=torch.uint8, device="cuda")
     out2 = np.zeros(2, np.uint32)
-    for seed, counter, base in ((0, 0, 0), (123, 77, 5000), ((9 << 32) + 4, (3 << 32) + 1, (1 << 33) + 17)):
+    for seed, counter, base in ((0, 0, 0), (123, 77, 5001), ((9 << 32) + 4, (3 << 32) + 1, (1 << 34) + 17)):
         _lib.check(lib.ml2048_sample_random_valid(valid.data_ptr(), acts.data_ptr(), m, base, seed, counter,
                                                   torch.cuda.current_stream().cuda_stream), "sample")
         got = acts.cpu().numpy()
@@ -718,10 +719,11 @@ def test_device_draws_equal_host_philox2x32(ml):
         for g in range(m):
             slot = base + g
             key = (seed & mask32) ^ (((seed >> 32) * 0x9E3779B9) & mask32)
-            c = np.array([slot & mask32, (counter & mask32) ^ (((counter >> 32) * 0x85EBCA6B) & mask32)
-                          ^ (((slot >> 32) * 0xC2B2AE35) & mask32)], np.uint32)
+            pair = slot >> 1
+            c = np.array([pair & mask32, (counter & mask32) ^ (((counter >> 32) * 0x85EBCA6B) & mask32)
+                          ^ (((pair >> 32) * 0xC2B2AE35) & mask32)], np.uint32)
             lib.ml2048_philox2x32_10(c.ctypes.data, key, out2.ctypes.data)
-            want[g] = int(out2[1]) >> 30
+            want[g] = int(out2[slot & 1]) >> 30
         np.testing.assert_array_equal(got, want)
 
 
