@@ -266,28 +266,38 @@ constexpr PolicySelTable make_policy_sel_table()
     return t;
 }
 
-// `sel` = the action's row of the table (16-byte aligned)
+// The move with its row of the table already fetched: words 0..3 in `sa`, 4..6 in `sb`.
 // Returns word 6 of the row (the direction, in the (mask, k)-indexed table).
+struct SelRow {
+    uint32_t in1a, in1b, in2a, in2b, out2a, out2b, action;
+};
+
+ML2048_FN uint32_t move_board_row(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, const SelRow &s, Fusions &f)
+{
+    // prmt_sign = the raw PRMT (no selector nibble of the table has its sign-replication bit set); __byte_perm would
+    // first mask a selector it cannot see to 0x7777
+    const uint32_t t0 = prmt_sign(r0, r2, s.in1a), t1 = prmt_sign(r1, r3, s.in1a), t2 = prmt_sign(r0, r2, s.in1b), t3 = prmt_sign(r1, r3, s.in1b);
+    uint32_t A = prmt_sign(t0, t1, s.in2a), B = prmt_sign(t0, t1, s.in2b), C = prmt_sign(t2, t3, s.in2a), D = prmt_sign(t2, t3, s.in2b);
+    push4(A, B, C, D, f);
+    const uint32_t u0 = prmt_sign(A, C, s.in2a), u1 = prmt_sign(B, D, s.in2a), u2 = prmt_sign(A, C, s.in2b), u3 = prmt_sign(B, D, s.in2b);
+    r0 = prmt_sign(u0, u1, s.out2a);
+    r1 = prmt_sign(u0, u1, s.out2b);
+    r2 = prmt_sign(u2, u3, s.out2a);
+    r3 = prmt_sign(u2, u3, s.out2b);
+    return s.action;
+}
+
+// `sel` = the action's row of the table in GLOBAL memory (16-byte aligned)
 ML2048_FN uint32_t move_board_sel(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, const uint32_t *sel, Fusions &f)
 {
 #if defined(__CUDACC__)
     const uint4 sa = __ldg(reinterpret_cast<const uint4 *>(sel));
     const uint4 sb = __ldg(reinterpret_cast<const uint4 *>(sel + 4));
-    const uint32_t in1a = sa.x, in1b = sa.y, in2a = sa.z, in2b = sa.w, out2a = sb.x, out2b = sb.y, row_action = sb.z;
+    const SelRow row{sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z};
 #else
-    const uint32_t in1a = sel[0], in1b = sel[1], in2a = sel[2], in2b = sel[3], out2a = sel[4], out2b = sel[5], row_action = sel[6];
+    const SelRow row{sel[0], sel[1], sel[2], sel[3], sel[4], sel[5], sel[6]};
 #endif
-    // prmt_sign = the raw PRMT (no selector nibble of the table has its sign-replication bit set); __byte_perm would
-    // first mask a selector it cannot see to 0x7777
-    const uint32_t t0 = prmt_sign(r0, r2, in1a), t1 = prmt_sign(r1, r3, in1a), t2 = prmt_sign(r0, r2, in1b), t3 = prmt_sign(r1, r3, in1b);
-    uint32_t A = prmt_sign(t0, t1, in2a), B = prmt_sign(t0, t1, in2b), C = prmt_sign(t2, t3, in2a), D = prmt_sign(t2, t3, in2b);
-    push4(A, B, C, D, f);
-    const uint32_t u0 = prmt_sign(A, C, in2a), u1 = prmt_sign(B, D, in2a), u2 = prmt_sign(A, C, in2b), u3 = prmt_sign(B, D, in2b);
-    r0 = prmt_sign(u0, u1, out2a);
-    r1 = prmt_sign(u0, u1, out2b);
-    r2 = prmt_sign(u2, u3, out2a);
-    r3 = prmt_sign(u2, u3, out2b);
-    return row_action;
+    return move_board_row(r0, r1, r2, r3, row, f);
 }
 
 #if !defined(__CUDACC__)
@@ -350,14 +360,21 @@ constexpr CellTable make_cell_table()
 __device__ const CellTable d_cell_one = make_cell_table();
 #endif
 
-ML2048_FN void put_cell(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t cell, uint32_t value)
-{
 #if defined(__CUDACC__)
-    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(d_cell_one.w) + cell);
+// ... with the cell's table entry already fetched
+ML2048_FN void put_cell_entry(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint4 t, uint32_t value)
+{
     r0 = t.x * value + r0;
     r1 = t.y * value + r1;
     r2 = t.z * value + r2;
     r3 = t.w * value + r3;
+}
+#endif
+
+ML2048_FN void put_cell(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t cell, uint32_t value)
+{
+#if defined(__CUDACC__)
+    put_cell_entry(r0, r1, r2, r3, __ldg(reinterpret_cast<const uint4 *>(d_cell_one.w) + cell), value);
 #else
     constexpr CellTable tab = make_cell_table();
     r0 += tab.w[4 * cell] * value;

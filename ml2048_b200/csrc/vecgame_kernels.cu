@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/ml2048_b200.h"
 #include "board_ops.cuh"
@@ -583,61 +584,116 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
 constexpr int kPairThreads = ML2048_PAIR_THREADS;
 constexpr int64_t kPairMinGames = 1 << 17;  // below this the batch is latency-bound: more, smaller threads win
 
+// What a launch draws once: the step's random schedule (scalar arguments, or the pre-drawn entry a CUDA graph replays).
+struct PairEnv {
+    int64_t rand_seed;
+    uint32_t two_mask;
+    uint64_t philox_counter;
+    const uint8_t *keys_table;
+};
+
+__device__ __forceinline__ PairEnv pair_env(const ml2048_step_args &a)
+{
+    PairEnv e{a.rand_seed, a.two_mask, a.philox_counter, a.randperm_keys};
+    if (a.sched) {
+        const int64_t cursor = *a.sched_cursor;
+        const ml2048_sched_entry s = a.sched[cursor];
+        e.rand_seed = s.rand_seed;
+        e.two_mask = s.two_mask;
+        e.philox_counter = s.philox_counter + 1ull;
+        e.keys_table += (int64_t)s.table * a.table_stride;
+        if (a.sched_cursor_next && blockIdx.x == 0 && threadIdx.x == 0) *a.sched_cursor_next = cursor + 1;
+    }
+    return e;
+}
+
+// What a thread reads of its two games before it can do anything: 56 bytes, three streams
+struct PairLoad {
+    uint4 bd[2];
+    uint32_t mask[2];
+    int2 ss[2];
+};
+
+// (Loading the three input streams with L1::no_allocate, to keep the lookup tables L1-resident, measured SLOWER -- 264 against
+// 240 us for the fused step at M = 2^24: the two games of a pair share 32-byte sectors, and the second load of each then
+// misses L1 as well.)
+template <typename T>
+__device__ __forceinline__ T load_stream(const T *p) { return *p; }
+
+template <bool kWantMask>
+__device__ __forceinline__ void pair_load(const ml2048_step_args &a, uint32_t g0, bool live0, bool live1, PairLoad &L)
+{
+    L.bd[0] = L.bd[1] = make_uint4(0, 0, 0, 0);
+    L.mask[0] = L.mask[1] = 1u;
+    L.ss[0] = L.ss[1] = make_int2(0, 0);
+    const uint4 *board_in = reinterpret_cast<const uint4 *>(a.board_in) + g0;
+    const uint32_t *valid_in = reinterpret_cast<const uint32_t *>(a.valid_in) + g0;
+    const int2 *step_score = reinterpret_cast<const int2 *>(a.step) + g0;
+    if (live0) {
+        L.bd[0] = load_stream(board_in);
+        if (kWantMask) L.mask[0] = load_stream(valid_in);
+        L.ss[0] = load_stream(step_score);
+    }
+    if (live1) {
+        L.bd[1] = load_stream(board_in + 1);
+        if (kWantMask) L.mask[1] = load_stream(valid_in + 1);
+        L.ss[1] = load_stream(step_score + 1);
+    }
+}
+
+// Where a game-step finds its lookup tables: the L1-resident copies in global memory.  (A policy class, so that a kernel
+// with the tables elsewhere can share pair_body: see the software-pipelined experiment below.)
+struct GlobalTables {
+    const uint4 *keys;  // spawn keys of the table epoch in force, 1024 rows
+    __device__ __forceinline__ SelRow policy_row(uint32_t index) const  // row of the (mask, k) table
+    {
+        const uint4 *row = reinterpret_cast<const uint4 *>(d_policy_sel.w) + index * 2u;
+        const uint4 sa = __ldg(row), sb = __ldg(row + 1);
+        return SelRow{sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z};
+    }
+    __device__ __forceinline__ SelRow move_row(uint32_t action) const
+    {
+        const uint4 *row = reinterpret_cast<const uint4 *>(d_move_sel) + action * 2u;
+        const uint4 sa = __ldg(row), sb = __ldg(row + 1);
+        return SelRow{sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z};
+    }
+    __device__ __forceinline__ uint4 keys_row(uint32_t row) const { return __ldg(keys + row); }
+    __device__ __forceinline__ uint4 cell_entry(uint32_t cell) const { return __ldg(reinterpret_cast<const uint4 *>(d_cell_one.w) + cell); }
+};
+
 // kRandom: the in-kernel random-valid policy (else caller-given actions); kNormalReward: reward_fn_normal (else the
 // reward kind is looked up at run time) -- compile-time switches for what is uniform over a launch, each worth a handful of
 // issue slots per game (parameter load, compare, branch).
-template <int kRng, bool kReset, bool kRandom, bool kNormalReward>
-__global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pair_kernel(const ml2048_step_args a)
+// All 32 lanes of a warp call this together (the fused auto-reset votes); a lane past the end of the batch has live0 = false.
+template <int kRng, bool kReset, bool kRandom, bool kNormalReward, class Tables>
+__device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairEnv &env, const Tables &tab, uint32_t g0, bool live0,
+                                          bool live1, PairLoad &L)
 {
-    const int64_t g0 = ((int64_t)blockIdx.x * kPairThreads + threadIdx.x) * 2;  // this thread owns games g0 and g0 + 1
-    if (g0 >= a.num_games) return;
-    const bool live1 = g0 + 1 < a.num_games;
-
-    int64_t rand_seed = a.rand_seed;
-    uint32_t two_mask = a.two_mask;
-    uint64_t philox_counter = a.philox_counter;
-    const uint8_t *keys_table = a.randperm_keys;
-    if (a.sched) {
-        const int64_t cursor = *a.sched_cursor;
-        const ml2048_sched_entry e = a.sched[cursor];
-        rand_seed = e.rand_seed;
-        two_mask = e.two_mask;
-        philox_counter = e.philox_counter + 1ull;
-        keys_table += (int64_t)e.table * a.table_stride;
-        if (a.sched_cursor_next && blockIdx.x == 0 && threadIdx.x == 0) *a.sched_cursor_next = cursor + 1;
-    }
+    const int64_t rand_seed = env.rand_seed;
+    const uint32_t two_mask = env.two_mask;
+    const uint64_t philox_counter = env.philox_counter;
 
     // one address per array; the second game of the pair is the next element
-    const uint4 *board_in = reinterpret_cast<const uint4 *>(a.board_in) + g0;
     uint4 *board_out = reinterpret_cast<uint4 *>(a.board_out) + g0;
     uint32_t *valid_out = reinterpret_cast<uint32_t *>(a.valid_out) + g0;
     int2 *step_score = reinterpret_cast<int2 *>(a.step) + g0;
     float *reward_out = a.reward + g0;
     uint8_t *terminated = a.terminated + g0, *invalid = a.invalid + g0;
 
-    uint4 bd[2];
-    bd[0] = board_in[0];
-    bd[1] = live1 ? board_in[1] : make_uint4(0, 0, 0, 0);
+    uint4 (&bd)[2] = L.bd;
+    uint32_t (&mask_now)[2] = L.mask;
+    int2 (&ss)[2] = L.ss;
     const bool want_mask = kReset || kRandom;
-    uint32_t mask_now[2] = {1u, 1u};
-    if (want_mask) {
-        const uint32_t *valid_in = reinterpret_cast<const uint32_t *>(a.valid_in) + g0;
-        mask_now[0] = valid_in[0];
-        if (live1) mask_now[1] = valid_in[1];
-    }
-    int2 ss[2];
-    ss[0] = step_score[0];
-    ss[1] = live1 ? step_score[1] : make_int2(0, 0);
 
     if (kReset) {
         // fused auto-reset (see step_kernel): lane l holds slots 2l and 2l+1 of the warp's 64, i.e. of TWO 32-slot groups
         // of the scan; ranks count the finished games of the lower lanes of the same half-warp, both games of each
-        const bool over0 = mask_now[0] == 0u, over1 = live1 && mask_now[1] == 0u;
+        const bool over0 = live0 && mask_now[0] == 0u, over1 = live1 && mask_now[1] == 0u;
         const uint32_t lanes0 = __ballot_sync(0xffffffffu, over0), lanes1 = __ballot_sync(0xffffffffu, over1);
         if (over0 || over1) {
             const uint32_t lane = threadIdx.x & 31u;
             const uint32_t lower = ((1u << lane) - 1u) & (0xffffu << (lane & 16u));
-            const uint32_t group = (uint32_t)g0 >> 5;
+            const uint32_t group = g0 >> 5;
             int32_t order = __ldg(a.reset_chunk_base + (group >> 10)) + __ldg(a.reset_rank + group) + __popc(lanes0 & lower) +
                             __popc(lanes1 & lower);
             PrepDraws d{a.rand_base, two_mask, a.prepare_philox_counter, a.randperm};
@@ -655,7 +711,7 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
                     reinterpret_cast<uint4 *>(const_cast<void *>(a.board_in))[g0 + j] = bd[j];
                     reinterpret_cast<uint32_t *>(const_cast<void *>(a.valid_in))[g0 + j] = mask_now[j];
                     a.id[g0 + j] = id_base + order;
-                    if (a.reset_indices && (int64_t)order < a.num_games) a.reset_indices[order] = g0 + j;
+                    if (a.reset_indices && (int64_t)order < a.num_games) a.reset_indices[order] = (int64_t)g0 + j;
                     if (a.age) a.age[g0 + j] = 0;
                     ss[j] = make_int2(0, 0);
                     order += 1;
@@ -663,6 +719,7 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
             }
         }
     }
+    if (!live0) return;
 
     // the uniform words of the two games: one Philox block per stream serves both when the thread's first global slot is
     // even (always, unless a shard starts at an odd slot)
@@ -690,21 +747,21 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         if (j == 1 && !live1) break;
-        const int64_t g = g0 + j;
+        const uint32_t g = g0 + j;
         const uint64_t slot = slot0 + j;
         const u32x2 rnd = {spawn_word[j], policy_word[j]};
         uint32_t action = 0u;
-        const uint32_t *sel_row;
+        SelRow sel_row;
         if (kRandom) {
             const uint32_t bits = mask_bits4(mask_now[j]);
-            sel_row = d_policy_sel.w + (bits * 4u + umulhi32(rnd.y, popc32(bits))) * kMoveSelRow;
+            sel_row = tab.policy_row(bits * 4u + umulhi32(rnd.y, popc32(bits)));
         } else {
             action = load_action(a.actions, a.action_dtype, g);
-            sel_row = d_move_sel + (action & 3u) * kMoveSelRow;
+            sel_row = tab.move_row(action & 3u);
         }
         uint32_t r0 = bd[j].x, r1 = bd[j].y, r2 = bd[j].z, r3 = bd[j].w;
         Fusions f;
-        const uint32_t row_action = move_board_sel(r0, r1, r2, r3, sel_row, f);
+        const uint32_t row_action = move_board_row(r0, r1, r2, r3, sel_row, f);
         if (kRandom) {
             action = row_action;
             if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
@@ -737,13 +794,13 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
             uint32_t cell;
             if (kRng == ML2048_RNG_REPLAY) {
                 const uint32_t row = ((uint32_t)rand_seed + (uint32_t)slot) & (uint32_t)(kRandRows - 1);
-                const uint4 keys = __ldg(reinterpret_cast<const uint4 *>(keys_table) + row);
+                const uint4 keys = tab.keys_row(row);
                 cell = first_empty_key(keys.x, keys.y, keys.z, keys.w, n0, n1, n2, n3) & 15u;
             } else {
                 const uint32_t empties = empties16(~n0 & kHi, ~n1 & kHi, ~n2 & kHi, ~n3 & kHi);
                 cell = kth_set_bit16(empties, umulhi32(rnd.x, popc32(empties)));
             }
-            put_cell(r0, r1, r2, r3, cell, 2u - ((two_mask >> cell) & 1u));
+            put_cell_entry(r0, r1, r2, r3, tab.cell_entry(cell), 2u - ((two_mask >> cell) & 1u));
             const uint32_t vm = valid_mask(r0, r1, r2, r3);
             const bool dead = vm == 0u;
             valid_out[j] = vm;
@@ -768,6 +825,33 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
         board_out[j] = make_uint4(r0, r1, r2, r3);
     }
 }
+
+// one pair per thread
+template <int kRng, bool kReset, bool kRandom, bool kNormalReward>
+__global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pair_kernel(const ml2048_step_args a)
+{
+    const uint32_t n = (uint32_t)a.num_games;  // < 2^31: launch_step
+    const uint32_t warp_first = (blockIdx.x * kPairThreads + (threadIdx.x & ~31u)) * 2u;
+    if (warp_first >= n) return;
+    const uint32_t g0 = (blockIdx.x * kPairThreads + threadIdx.x) * 2u;  // this thread owns games g0 and g0 + 1
+    const bool live0 = g0 < n, live1 = g0 + 1u < n;
+    const PairEnv env = pair_env(a);
+    PairLoad L;
+    pair_load<kReset || kRandom>(a, g0, live0, live1, L);
+    const GlobalTables tab{reinterpret_cast<const uint4 *>(env.keys_table)};
+    pair_body<kRng, kReset, kRandom, kNormalReward>(a, env, tab, g0, live0, live1, L);
+}
+
+// A software-pipelined variant of this kernel was built and measured in round 2 and is NOT kept (profiles/pair_loop_experiments_r02.txt): a
+// GPU-filling grid striding over the batch, every thread prefetching the 56 input bytes of its next pair while it plays the
+// current one.  (1) Prefetch into registers (56 registers, 9 blocks per SM): 293 us against 240 us for the fused step at
+// M = 2^24 -- ptxas put the prefetch on a scoreboard that loads of the body share, so the first of them waits for the DRAM round
+// trip anyway (ncu: 20 % of all stall samples on that one instruction).  (2) Prefetch with cp.async into shared memory (no
+// destination registers, 40 registers, every thread waiting only for its own copies): 328 us -- the staging buffers leave
+// little L1 and the table lookups in the middle of every dependency chain then miss it.  (3) The same with the tables in
+// shared memory as well (512-thread blocks, one buffer): 324 us, issue slots 51 % busy against 66 %: with the DRAM waits gone
+// the warps wait for the reset path's dependent loads, the shared-memory lookups (`short scoreboard` 2.5 warps per issue)
+// and the LSU queue (`mio throttle`) instead.  One pair per thread with twelve 128-thread blocks per SM stays the fastest.
 
 // ---- auto-reset (VecGame.prepare, game_numba.py:619-658) -----------------------------------
 // Pass 1: terminated games per tile of 4096 slots.  Pass 2: exclusive scan over tiles (one block),
@@ -1364,15 +1448,16 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
 }
 
 // ML2048_STEP=single in the environment keeps large lean batches on the one-game-per-thread kernel (A/B measurements and the
-// differential test of the two kernels); read once, or on every call when ML2048_PREPARE_RECHECK is set.
-inline bool force_single_step()
+// differential test of the two kernels).  Read once, or on every call when ML2048_PREPARE_RECHECK is set.
+inline bool step_mode_is(const char *what)
 {
     static const bool recheck = getenv("ML2048_PREPARE_RECHECK") != nullptr;
-    static const bool single_at_start = [] { const char *m = getenv("ML2048_STEP"); return m && m[0] == 's'; }();
-    if (!recheck) return single_at_start;
-    const char *m = getenv("ML2048_STEP");
-    return m && m[0] == 's';
+    static const char *at_start = [] { const char *m = getenv("ML2048_STEP"); return m ? strdup(m) : (const char *)nullptr; }();
+    const char *m = recheck ? getenv("ML2048_STEP") : at_start;
+    return m && strcmp(m, what) == 0;
 }
+
+inline bool force_single_step() { return step_mode_is("single"); }
 
 template <int kRng>
 int launch_step(const ml2048_step_args &a, cudaStream_t s)
@@ -1380,22 +1465,23 @@ int launch_step(const ml2048_step_args &a, cudaStream_t s)
     const bool full = a.action_mode == ML2048_ACTIONS_FROM_LOGITS || a.episode_max_tile || a.traj_state || a.tr_state || a.tr_valid_actions ||
                       a.tr_action || a.tr_reward || a.tr_next_state || a.tr_next_valid_actions || a.tr_step || a.tr_terminated;
     const int onehot_kind = a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE;
-    if (!full && !a.merged && onehot_kind == ML2048_ONEHOT_NONE && a.num_games >= kPairMinGames && !force_single_step()) {
+    if (!full && !a.merged && onehot_kind == ML2048_ONEHOT_NONE && a.num_games >= kPairMinGames && a.num_games < (1ll << 31) && !force_single_step()) {
         // the lean core-only configuration at large batches: two games per thread
         const unsigned grid = (unsigned)(((a.num_games + 1) / 2 + kPairThreads - 1) / kPairThreads);
         clear_stale_error();
         const bool normal = a.reward_kind == ML2048_REWARD_NORMAL;
         const bool random = a.action_mode == ML2048_ACTIONS_RANDOM_VALID;
-        if (a.reset_rank) {  // the fused auto-reset implies the random policy (checked by ml2048_step)
-            if (normal) step_pair_kernel<kRng, true, true, true><<<grid, kPairThreads, 0, s>>>(a);
-            else step_pair_kernel<kRng, true, true, false><<<grid, kPairThreads, 0, s>>>(a);
-        } else if (random) {
-            if (normal) step_pair_kernel<kRng, false, true, true><<<grid, kPairThreads, 0, s>>>(a);
-            else step_pair_kernel<kRng, false, true, false><<<grid, kPairThreads, 0, s>>>(a);
-        } else {
-            if (normal) step_pair_kernel<kRng, false, false, true><<<grid, kPairThreads, 0, s>>>(a);
-            else step_pair_kernel<kRng, false, false, false><<<grid, kPairThreads, 0, s>>>(a);
+        const int variant = (a.reset_rank ? 4 : random ? 2 : 0) + (normal ? 1 : 0);  // the fused auto-reset implies the random policy
+#define ML2048_PAIR_LAUNCH(RESET, RANDOM, NORMAL) step_pair_kernel<kRng, RESET, RANDOM, NORMAL><<<grid, kPairThreads, 0, s>>>(a)
+        switch (variant) {
+        case 5: ML2048_PAIR_LAUNCH(true, true, true); break;
+        case 4: ML2048_PAIR_LAUNCH(true, true, false); break;
+        case 3: ML2048_PAIR_LAUNCH(false, true, true); break;
+        case 2: ML2048_PAIR_LAUNCH(false, true, false); break;
+        case 1: ML2048_PAIR_LAUNCH(false, false, true); break;
+        default: ML2048_PAIR_LAUNCH(false, false, false); break;
         }
+#undef ML2048_PAIR_LAUNCH
         return launch_status();
     }
     if (a.reset_rank) {

@@ -14,7 +14,6 @@ import torch
 pytestmark = pytest.mark.gpu
 
 PAIR_MIN = 1 << 17  # kPairMinGames
-STATE = ("_board", "_valid", "_id", "_step_score", "_reward", "_terminated_padded", "_invalid", "_reset_count_dev", "_game_count_dev")
 
 
 @pytest.fixture(scope="module")
@@ -37,7 +36,7 @@ def same_state(a, b, what):
 
 @pytest.mark.parametrize("rng_mode", ["replay", "philox"])
 @pytest.mark.parametrize("fused", [False, True])
-@pytest.mark.parametrize("m", [PAIR_MIN, PAIR_MIN + 1, PAIR_MIN + 37, (1 << 19) + 5])
+@pytest.mark.parametrize("m", [PAIR_MIN, PAIR_MIN + 1, PAIR_MIN + 37, (1 << 19) + 5, (1 << 20) + 77])
 def test_pair_kernel_equals_single_kernel_random_policy(ml, monkeypatch, rng_mode, fused, m):
     kw = dict(rng_mode=rng_mode, output="torch", track_merged=False, sync_free=True)
     monkeypatch.setenv("ML2048_STEP", "pair")
