@@ -14,6 +14,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 PAIR_MIN = 1 << 17  # kPairMinGames
+STATE = ("_board", "_valid", "_id", "_step_score", "_reward", "_terminated_padded", "_invalid", "_reset_count_dev", "_game_count_dev")
 
 
 @pytest.fixture(scope="module")
