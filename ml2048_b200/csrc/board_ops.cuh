@@ -384,6 +384,19 @@ ML2048_FN void put_cell(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, 
 #endif
 }
 
+// The same without the table: one 64-bit shift places the value inside its half of the board, one predicate picks the half.
+// For the latency-bound small-batch kernels, where a dependent load from a cold table costs more than ten ALU instructions.
+ML2048_FN void put_cell_shift(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t cell, uint32_t value)
+{
+    const unsigned long long v = (unsigned long long)value << ((cell & 7u) * 8u);
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const bool top = (cell & 8u) != 0u;
+    r0 += top ? 0u : lo;
+    r1 += top ? 0u : hi;
+    r2 += top ? lo : 0u;
+    r3 += top ? hi : 0u;
+}
+
 // Replay-mode spawn position.  The reference walks row `p` of randperm and takes the first entry whose
 // cell is empty (_spawn2, game_numba.py:198-204).  Equivalently: among the empty cells take the one with
 // the smallest RANK in that row.  `keys` is the row in inverse form, keys[c] = 16*rank(c) + c (see

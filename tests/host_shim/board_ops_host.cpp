@@ -67,7 +67,10 @@ void hs_put_cell(uint8_t *board16, uint32_t cell, uint32_t value)
 {
     uint32_t r[4];
     memcpy(r, board16, 16);
+    uint32_t q[4] = {r[0], r[1], r[2], r[3]};
     put_cell(r[0], r[1], r[2], r[3], cell, value);
+    put_cell_shift(q[0], q[1], q[2], q[3], cell, value);
+    if (memcmp(q, r, 16) != 0) r[0] = r[1] = r[2] = r[3] = 0xffffffffu;  // the two forms must agree (the test then fails on the board)
     memcpy(board16, r, 16);
 }
 
