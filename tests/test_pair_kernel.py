@@ -106,3 +106,28 @@ def test_pair_kernel_fused_rollout_against_the_oracle(ml, oracle, monkeypatch):
             np.testing.assert_array_equal(res["score"].cpu().numpy().view(np.uint32), want["score"].view(np.uint32))
             np.testing.assert_array_equal(env._id.cpu().numpy(), ref._data["id"])
     assert env._game_count == ref._game_count > 2 * m
+
+
+@pytest.mark.parametrize("rng_mode", ["replay", "philox"])
+def test_pair_kernel_shard_at_an_odd_slot(ml, monkeypatch, rng_mode):
+    """A Philox block serves a PAIR of global slots (slot >> 1).  A shard that starts at an odd global slot has its threads'
+    two games in two different blocks: its draws (policy words, Philox spawn cells) must still be those of the whole batch."""
+    monkeypatch.setenv("ML2048_STEP", "pair")
+    cut = PAIR_MIN + 1  # odd: the second shard's first slot
+    m = cut + PAIR_MIN + 2
+    kw = dict(rng_mode=rng_mode, output="torch", track_merged=False, sync_free=True)
+    whole = ml.VecGame(m, "improved", **kw)
+    parts = [ml.VecGame(cut, "improved", slot_base=0, **kw), ml.VecGame(m - cut, "improved", slot_base=cut, **kw)]
+    for e in [whole] + parts:
+        e.reset(17)
+    for t in range(130):
+        for e in [whole] + parts:
+            e.step_random(return_actions=True, auto_reset=True)
+        if t < 2 or t % 32 == 0 or t == 129:
+            for name in ("_step_score", "_reward", "_invalid"):
+                assert torch.equal(torch.cat([getattr(p, name) for p in parts]), getattr(whole, name)), (name, t)
+            assert torch.equal(torch.cat([p._terminated_padded[: p._size] for p in parts]), whole._terminated_padded[:m]), t
+            assert torch.equal(torch.cat([p.sampled_actions for p in parts]), whole.sampled_actions), t
+            for k in (0, 1):
+                assert torch.equal(torch.cat([p.observations()[k] for p in parts]), whole.observations()[k]), (k, t)
+    assert whole.episode_stats()["episodes"] == sum(p.episode_stats()["episodes"] for p in parts) > m // 4
