@@ -48,7 +48,9 @@ enum { ML2048_REWARD_NORMAL = 0, ML2048_REWARD_IMPROVED = 1, ML2048_REWARD_RANK 
 /* where spawn randomness comes from */
 enum {
     ML2048_RNG_REPLAY = 0, /* the reference's pre-drawn tables: bit-exact (game_numba.py:172-212) */
-    ML2048_RNG_PHILOX = 1  /* counter-based Philox4x32-10 keyed by (seed, global slot, step counter) */
+    ML2048_RNG_PHILOX = 1  /* counter-based: Philox2x32-10 blocks keyed by the seed, counter = (global slot >> 1, step counter);
+                              a block's two words serve the two slots of a pair (even slot: word 0, odd slot: word 1).  Separate
+                              streams (key ^ tag) for the policy's words, the spawn cells and the auto-reset's cells */
 };
 
 /* element type of the `actions` array */
@@ -287,7 +289,8 @@ ML2048_API int ml2048_valid_actions(const void *board, void *valid_out, int64_t 
  * hist20 is [20] unsigned long long, accumulated (not cleared). */
 ML2048_API int ml2048_max_tile_hist(const void *board, const uint8_t *terminated, int64_t num_games, unsigned long long *hist20, void *stream);
 
-/* uniform-over-valid action sampler (policy/random.py:17-27) as a stand-alone op */
+/* uniform-over-valid action sampler (policy/random.py:17-27) as a stand-alone op: draws the policy-stream word of
+ * (philox_seed, slot_base + i, philox_counter), i.e. the action ML2048_ACTIONS_RANDOM_VALID picks inside ml2048_step */
 ML2048_API int ml2048_sample_random_valid(const void *valid, uint8_t *actions_out, int64_t num_games, int64_t slot_base,
                                uint64_t philox_seed, uint64_t philox_counter, void *stream);
 
