@@ -687,8 +687,9 @@ __device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairE
     const bool want_mask = kReset || kRandom;
     // With the auto-reset fused in every game moves, so the five narrow results of the pair are known together and go out as
     // ONE store per array (8 + 8 + 16 + 2 + 2 bytes) when the arrays are aligned for it: five store instructions and their
-    // address arithmetic less per pair (237 against 239.5 us at M = 2^24).  Not in Philox mode, whose extra live values then spill:
-    // 252 against 245 us.
+    // address arithmetic less per pair (237 against 239.5 us at M = 2^24).  Not in Philox mode, whose extra live values then spill
+    // (252 against 245 us), and not for the variants without the fused reset, where holding the first game's results until the
+    // second one is known to have moved costs more than the stores (given actions 213 against 198 us).
     constexpr bool kPairStores = kReset && kRng == ML2048_RNG_REPLAY;
     const bool pair_stores = kPairStores && live1 &&
                              ((reinterpret_cast<uintptr_t>(a.valid_out) | reinterpret_cast<uintptr_t>(a.reward)) & 7u) == 0u &&
