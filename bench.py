@@ -697,13 +697,18 @@ def run_b200_arm(args: argparse.Namespace) -> None:
         env.configure(output="numpy", sync_free=False)
         consumed = 0
 
+        result_bytes = [0]
+
         def e2e_step(t: int) -> int:
             (idx,) = env.prepare()                # D2H: reset count + indices
             keys = ("state", "valid_actions", "reward", "terminated")  # D2H: what a rollout consumer reads
             res = env.step(host_actions[t], fetch=keys)  # H2D: M action bytes
-            got = 0
-            for key in keys:
-                got += res[key].nbytes
+            # bytes that crossed PCIe towards the host: the environment reports what it copied (valid_actions + terminated travel
+            # as ONE packed byte per game and are expanded on the host, inside this timed call); else the arrays themselves
+            got = getattr(env, "last_step_d2h_bytes", None)
+            if got is None:
+                got = sum(res[key].nbytes for key in keys)
+            result_bytes[0] = sum(res[key].nbytes for key in keys) + idx.nbytes + 8
             return got + idx.nbytes + 8
 
         for t in range(warm):
@@ -742,6 +747,10 @@ def run_b200_arm(args: argparse.Namespace) -> None:
             "unit": UNIT,
             "h2d_bytes_per_step": h2d_step,
             "d2h_bytes_per_step": d2h_step,
+            "result_bytes_per_step": int(result_bytes[0] * world),
+            "d2h_note": "d2h_bytes_per_step = bytes copied device->host per step (board 16 B, reward 4 B, valid_actions + terminated as one "
+                        "packed byte per game, reset indices); result_bytes_per_step = the host arrays the caller receives (25 B per game), "
+                        "rebuilt from the packed byte by host threads inside the timed step",
             "ms_per_step": e2e_ms / k_steps,
             "invalid_moves_in_last_step": invalid_last,
             "light": {"value": world * m / (light_ms * 1e-3), "ms_per_step": light_ms,

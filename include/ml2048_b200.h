@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ML2048_ABI_VERSION 9
+#define ML2048_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define ML2048_API __attribute__((visibility("default")))
@@ -288,6 +288,20 @@ ML2048_API int ml2048_valid_actions(const void *board, void *valid_out, int64_t 
  * with terminated == null: VecGame.summary's histogram over all live boards (game_numba.py:593-596).
  * hist20 is [20] unsigned long long, accumulated (not cleared). */
 ML2048_API int ml2048_max_tile_hist(const void *board, const uint8_t *terminated, int64_t num_games, unsigned long long *hist20, void *stream);
+
+/* The result flags of a step for a HOST caller, one byte per game: bits 0..3 = valid_actions (left, right, up, down;
+ * game_numba.py:540), bit 4 = terminated (:546), bit 5 = invalid (:547).  `terminated` / `invalid` may be null (bits 0).
+ * VecGame.step(host actions, fetch=...) ships this byte over PCIe instead of the six bytes of the three arrays and rebuilds
+ * them with ml2048_unpack_flags (host code; `threads` worker threads, any of the three outputs may be null). */
+ML2048_API int ml2048_pack_flags(const void *valid, const uint8_t *terminated, const uint8_t *invalid, uint8_t *packed, int64_t num_games,
+                                 void *stream);
+ML2048_API void ml2048_unpack_flags(const uint8_t *host_packed, int64_t num_games, uint8_t *host_valid4, uint8_t *host_terminated,
+                                    uint8_t *host_invalid, int32_t threads);
+/* ... for a result that arrives in slices [slice_lo[k], slice_hi[k]): events[k] is the cudaEvent_t recorded after slice k's packed
+ * bytes were copied (null = already there).  The worker threads wait for the events themselves; returns 0 or a cudaError_t. */
+ML2048_API int ml2048_unpack_flags_sliced(const uint8_t *host_packed, int32_t num_slices, const int64_t *slice_lo, const int64_t *slice_hi,
+                                          void *const *events, uint8_t *host_valid4, uint8_t *host_terminated, uint8_t *host_invalid,
+                                          int32_t threads);
 
 /* uniform-over-valid action sampler (policy/random.py:17-27) as a stand-alone op: draws the policy-stream word of
  * (philox_seed, slot_base + i, philox_counter), i.e. the action ML2048_ACTIONS_RANDOM_VALID picks inside ml2048_step */

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # the full ABI like the default library
 LIB_PATH = os.environ.get("ML2048_LIB") or os.path.join(_HERE, "libml2048_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 STATS_REPLICAS = 64
 STATS_WORDS = 24  # 20 histogram bins + episodes, score_sum, step_sum, score_max (unsigned long long each)
 
@@ -163,6 +163,9 @@ SYMBOLS = {
     "ml2048_encode_onehot": (C.c_int, [_VP, _VP, _I32, _I64, _VP]),
     "ml2048_valid_actions": (C.c_int, [_VP, _VP, _I64, _VP]),
     "ml2048_max_tile_hist": (C.c_int, [_VP, _VP, _I64, _VP, _VP]),
+    "ml2048_pack_flags": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _VP]),
+    "ml2048_unpack_flags": (None, [_VP, _I64, _VP, _VP, _VP, _I32]),
+    "ml2048_unpack_flags_sliced": (C.c_int, [_VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _I32]),
     "ml2048_sample_random_valid": (C.c_int, [_VP, _VP, _I64, _I64, _U64, _U64, _VP]),
     "ml2048_sample_masked_categorical": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _U64, _U64, _VP]),
     "ml2048_gae": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _I64, C.c_float, C.c_float, _VP]),

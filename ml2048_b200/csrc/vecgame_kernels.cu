@@ -1391,6 +1391,27 @@ __global__ void __launch_bounds__(kStepThreads) gae_kernel(const float *v0, cons
     }
 }
 
+// The flags a host caller reads after a step -- valid_actions (four 0/1 bytes), terminated, invalid -- as ONE byte per game for
+// the trip over PCIe: bits 0..3 = left, right, up, down valid, bit 4 = terminated, bit 5 = invalid.  Four games per thread.
+__global__ void __launch_bounds__(kStepThreads) pack_flags_kernel(const uint32_t *valid, const uint8_t *terminated, const uint8_t *invalid,
+                                                                  uint8_t *packed, int64_t num_games)
+{
+    const int64_t g = ((int64_t)blockIdx.x * kStepThreads + threadIdx.x) * 4;
+    if (g >= num_games) return;
+    const bool whole = g + 4 <= num_games && ((reinterpret_cast<uintptr_t>(valid) & 15u) | (reinterpret_cast<uintptr_t>(packed) & 3u) |
+                                               (reinterpret_cast<uintptr_t>(terminated) & 3u) | (reinterpret_cast<uintptr_t>(invalid) & 3u)) == 0u;
+    if (whole) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(valid + g);
+        uint32_t out = mask_bits4(v.x) | (mask_bits4(v.y) << 8) | (mask_bits4(v.z) << 16) | (mask_bits4(v.w) << 24);
+        if (terminated) out |= (*reinterpret_cast<const uint32_t *>(terminated + g) & 0x01010101u) << 4;
+        if (invalid) out |= (*reinterpret_cast<const uint32_t *>(invalid + g) & 0x01010101u) << 5;
+        *reinterpret_cast<uint32_t *>(packed + g) = out;
+    } else {
+        for (int64_t i = g; i < num_games && i < g + 4; ++i)
+            packed[i] = (uint8_t)(mask_bits4(valid[i]) | (terminated ? (terminated[i] & 1u) << 4 : 0u) | (invalid ? (invalid[i] & 1u) << 5 : 0u));
+    }
+}
+
 __global__ void fill_terminated_kernel(uint8_t *terminated, int64_t num_games, int64_t padded)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1805,6 +1826,18 @@ int ml2048_valid_actions(const void *board, void *valid_out, int64_t num_games, 
     clear_stale_error();
     valid_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4 *>(board),
                                                                                 reinterpret_cast<uint32_t *>(valid_out), num_games);
+    return launch_status();
+}
+
+int ml2048_pack_flags(const void *valid, const uint8_t *terminated, const uint8_t *invalid, uint8_t *packed, int64_t num_games, void *stream)
+{
+    if (num_games <= 0) return ML2048_E_SIZE;
+    if (!valid || !packed) return ML2048_E_NULL;
+    if (misaligned(valid, 4)) return ML2048_E_ALIGN;
+    const unsigned grid = (unsigned)(((num_games + 3) / 4 + kStepThreads - 1) / kStepThreads);
+    clear_stale_error();
+    pack_flags_kernel<<<grid, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint32_t *>(valid), terminated, invalid,
+                                                                                  packed, num_games);
     return launch_status();
 }
 

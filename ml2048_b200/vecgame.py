@@ -28,6 +28,7 @@ Keyword-only extras (not in the reference):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Optional
 
 import numpy as np
@@ -1026,6 +1027,10 @@ class VecGame:
 
     _PIPELINE_MIN_GAMES = 1 << 18
     _PIPELINE_CHUNKS = 8
+    _PACK_FLAGS = os.environ.get("ML2048_PACK_FLAGS", "1") != "0"  # one byte per game over PCIe for mask + terminated + invalid
+    # host threads that expand a slice of packed flags: a share of the host's cores (one process per GPU shares them)
+    _UNPACK_THREADS = int(os.environ.get("ML2048_UNPACK_THREADS", "0")) or max(
+        1, min(4, (os.cpu_count() or 4) // (2 * max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))))  # (2-4 measured best; more only contend)
 
     def _can_pipeline(self, actions) -> bool:
         if self._output != "numpy" or self._sched_len or self._size < self._PIPELINE_MIN_GAMES:
@@ -1071,6 +1076,19 @@ class VecGame:
                 buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                 self._host[k] = buf
             host[k] = buf
+        # valid_actions (4 bytes), terminated and invalid cross PCIe as ONE byte per game (ml2048_pack_flags on the device,
+        # ml2048_unpack_flags on the host, slice by slice while the later slices are still in flight): the D2H stream is what
+        # bounds this path, and the three arrays are 6 of the 26 bytes a game's full result takes
+        # (only when the 4-byte mask is wanted: terminated / invalid alone are a byte each already)
+        flag_keys = [k for k in ("valid_actions", "terminated", "invalid") if k in fields] if self._PACK_FLAGS and "valid_actions" in fields else []
+        packed_dev = packed_host = None
+        if flag_keys:
+            packed_dev = getattr(self, "_pipe_packed", None)
+            if packed_dev is None:
+                packed_dev = self._pipe_packed = torch.empty((m,), dtype=torch.uint8, device=self.device)
+                self._pipe_packed_host = torch.empty((m,), dtype=torch.uint8, pin_memory=True)
+            packed_host = self._pipe_packed_host
+        slices = []
         a = _lib.StepArgs.from_buffer_copy(self._step_args)
         a.action_mode, a.action_dtype, a.actions_out, a.sched = _lib.ACTIONS_GIVEN, code, None, None
         a.reset_rank = None  # (left over from an earlier step_random(auto_reset=True))
@@ -1108,11 +1126,33 @@ class VecGame:
                 if self._step_args.age:
                     a.age = self._age.data_ptr() + 4 * lo
                 _lib.check(self._lib.ml2048_step(C.byref(a), raw_main), "ml2048_step")
+                if flag_keys:
+                    _lib.check(self._lib.ml2048_pack_flags(
+                        a.valid_out, a.terminated if "terminated" in fields else None, a.invalid if "invalid" in fields else None,
+                        packed_dev.data_ptr() + lo, hi - lo, raw_main), "ml2048_pack_flags")
                 d2h.wait_stream(main)
                 with torch.cuda.stream(d2h):
+                    if flag_keys:
+                        packed_host[lo:hi].copy_(packed_dev[lo:hi], non_blocking=True)
+                        done = torch.cuda.Event()
+                        done.record(d2h)
+                        slices.append((lo, hi, done))
                     for k, t in fields.items():
-                        host[k][lo:hi].copy_(t[lo:hi], non_blocking=True)
+                        if k not in flag_keys:
+                            host[k][lo:hi].copy_(t[lo:hi], non_blocking=True)
         self._cur = 1 - cur  # only now: an exception above leaves the ping-pong state where it was
+        # bytes this call moves over PCIe towards the host (for callers that account for them: bench.py's e2e)
+        self.last_step_d2h_bytes = sum(t.numel() * t.element_size() for k, t in fields.items() if k not in flag_keys) + (m if flag_keys else 0)
+        if flag_keys:
+            ptr = {k: (host[k].data_ptr() if k in fields else None) for k in ("valid_actions", "terminated", "invalid")}
+            n = len(slices)
+            lo_arr = (C.c_int64 * n)(*[sl[0] for sl in slices])
+            hi_arr = (C.c_int64 * n)(*[sl[1] for sl in slices])
+            ev_arr = (C.c_void_p * n)(*[sl[2].cuda_event for sl in slices])
+            # one call: the library's worker threads wait for each slice's event themselves and expand it while the slices
+            # behind it are still in flight
+            _lib.check(self._lib.ml2048_unpack_flags_sliced(packed_host.data_ptr(), n, lo_arr, hi_arr, ev_arr, ptr["valid_actions"],
+                                                            ptr["terminated"], ptr["invalid"], self._UNPACK_THREADS), "ml2048_unpack_flags_sliced")
         d2h.synchronize()
         res = VecStepResult(self)
         for k in fetch:

@@ -198,3 +198,26 @@ def test_pack_randperm_keys(lib):
     bad[3, 0] = bad[3, 1]
     assert lib.ml2048_pack_randperm_keys(bad.ctypes.data, keys.ctypes.data, 1024) == -4
     assert lib.ml2048_pack_randperm_keys(None, keys.ctypes.data, 1024) == -1
+
+
+def test_unpack_flags_host(lib):
+    """ml2048_unpack_flags (host code): one packed byte per game -> valid_actions[4], terminated, invalid; every size class of the
+    vector / word / scalar loops, any subset of the outputs, any thread count; bytes next to the outputs stay untouched."""
+    rng = np.random.default_rng(1)
+    for n in (1, 7, 8, 9, 63, 64, 65, 1000, (1 << 17) + 5, (1 << 20) + 3):
+        p = rng.integers(0, 256, n).astype(np.uint8)
+        for threads in (0, 1, 3, 16):
+            v = np.full((n + 2, 4), 7, np.uint8)
+            t = np.full(n + 2, 7, np.uint8)
+            i = np.full(n + 2, 7, np.uint8)
+            lib.ml2048_unpack_flags(p.ctypes.data, n, v[1:].ctypes.data, t[1:].ctypes.data, i[1:].ctypes.data, threads)
+            np.testing.assert_array_equal(v[1:-1], (p[:, None] >> np.arange(4)) & 1)
+            np.testing.assert_array_equal(t[1:-1], (p >> 4) & 1)
+            np.testing.assert_array_equal(i[1:-1], (p >> 5) & 1)
+            assert (v[0] == 7).all() and (v[-1] == 7).all() and t[0] == t[-1] == i[0] == i[-1] == 7
+        t = np.full(n, 7, np.uint8)
+        lib.ml2048_unpack_flags(p.ctypes.data, n, None, t.ctypes.data, None, 2)
+        np.testing.assert_array_equal(t, (p >> 4) & 1)
+    lib.ml2048_unpack_flags(None, 10, None, None, None, 1)  # nothing to do, no crash
+    assert lib.ml2048_pack_flags(None, None, None, None, 10, None) == -1
+    assert lib.ml2048_pack_flags(1 << 20, None, None, 1 << 21, 0, None) == -3

@@ -591,10 +591,16 @@ def test_pipelined_host_step_matches_plain_step(ml, oracle):
         ref.prepare()
         env.prepare()
         acts = oracle.random_valid_actions(ref.observations()[1], rng.random(m))
+        if t % 3 == 2:
+            acts[::5] = (acts[::5] + 1) % 4  # some of these are invalid moves
         r0 = ref.step(acts)
         host_acts = torch.from_numpy(acts.astype(np.uint8 if t % 2 else np.int64)).pin_memory()
-        r1 = env.step(host_acts, fetch=keys)
+        # (valid_actions / terminated / invalid travel as one packed byte per game: every combination of the three is fetched)
+        fetched = keys + (("invalid",) if t % 2 else ()) if t < 8 else tuple(k for k in keys if k != ("valid_actions", "terminated")[t % 2])
+        r1 = env.step(host_acts, fetch=fetched)
+        keys_now, keys = keys, fetched
         assert all(dict.__contains__(r1, k) for k in keys), "fetched keys must be pre-populated"
+        keys = keys_now
         for k in keys + ("step", "invalid", "prev_valid_actions"):
             np.testing.assert_array_equal(r1[k], r0[k], err_msg=f"{k} step {t}")
     oh = env.observations_onehot().cpu().numpy()
@@ -825,3 +831,30 @@ def test_two_devices_in_one_process_large_onehot(ml):
         torch.cuda.synchronize(d)
     assert torch.equal(envs[0].observations()[0].cpu(), envs[1].observations()[0].cpu())
     assert torch.equal(envs[0].observations_onehot().cpu(), envs[1].observations_onehot().cpu())
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1023, 4096, 100003])
+def test_pack_flags_kernel(ml, n):
+    """ml2048_pack_flags through the raw C ABI: bits 0..3 = the four valid-action bytes, bit 4 = terminated, bit 5 = invalid; sizes
+    that are not multiples of four, slices that start at odd offsets (the scalar path), absent terminated / invalid."""
+    from ml2048_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    valid = torch.randint(0, 2, (n + 8, 4), dtype=torch.uint8, device="cuda", generator=g)
+    term = torch.randint(0, 2, (n + 8,), dtype=torch.uint8, device="cuda", generator=g)
+    inv = torch.randint(0, 2, (n + 8,), dtype=torch.uint8, device="cuda", generator=g)
+    stream = torch.cuda.current_stream().cuda_stream
+    for off in (0, 1, 4):
+        for with_term, with_inv in ((True, True), (True, False), (False, False)):
+            out = torch.full((n + 8,), 0xAA, dtype=torch.uint8, device="cuda")
+            _lib.check(lib.ml2048_pack_flags(valid.data_ptr() + 4 * off, term.data_ptr() + off if with_term else None,
+                                             inv.data_ptr() + off if with_inv else None, out.data_ptr() + off, n, stream), "pack")
+            v = valid[off:off + n].to(torch.int32)
+            want = v[:, 0] | (v[:, 1] << 1) | (v[:, 2] << 2) | (v[:, 3] << 3)
+            if with_term:
+                want = want | (term[off:off + n].to(torch.int32) << 4)
+            if with_inv:
+                want = want | (inv[off:off + n].to(torch.int32) << 5)
+            assert torch.equal(out[off:off + n].to(torch.int32), want), (off, with_term, with_inv)
+            assert (out[:off] == 0xAA).all() and (out[off + n:] == 0xAA).all()
