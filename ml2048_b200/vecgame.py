@@ -1026,7 +1026,7 @@ class VecGame:
     # -- host-buffer pipeline -----------------------------------------------------------------------
 
     _PIPELINE_MIN_GAMES = 1 << 18
-    _PIPELINE_CHUNKS = 8
+    _PIPELINE_CHUNKS = int(os.environ.get("ML2048_PIPELINE_CHUNKS", "8"))  # slices of the H2D / kernel / D2H pipeline
     _PACK_FLAGS = os.environ.get("ML2048_PACK_FLAGS", "1") != "0"  # one byte per game over PCIe for mask + terminated + invalid
     # host threads that expand a slice of packed flags: a share of the host's cores (one process per GPU shares them)
     _UNPACK_THREADS = int(os.environ.get("ML2048_UNPACK_THREADS", "0")) or max(
