@@ -562,6 +562,24 @@ ML2048_FN u32x2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k)
     return u32x2{c0, c1};
 }
 
+// The same rounds with the ten round keys handed in (key + i * W): a kernel whose host code knows the seed passes them as
+// kernel parameters, and the rounds then read them straight from the constant bank instead of deriving them once per warp.
+struct PhiloxKeys {
+    uint32_t k[10];
+};
+
+ML2048_FN u32x2 philox2x32_10_keys(uint32_t c0, uint32_t c1, const PhiloxKeys &keys)
+{
+    const uint32_t M = 0xD256D193u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi = umulhi32(M, c0), lo = M * c0;
+        c0 = hi ^ keys.k[i] ^ c1;
+        c1 = lo;
+    }
+    return u32x2{c0, c1};
+}
+
 // One Philox2x32-10 block of stream `tag` (0 = the policy's words, kSpawnStream = the spawn cells of Philox mode, kResetStream
 // = the auto-reset's two cells): counter = (index low word, counter low word ^ high words * odd constants), key = seed ^ tag.
 // The key depends on nothing but the seed (a kernel parameter), so its ten round values are computed once per warp on the
@@ -570,11 +588,36 @@ ML2048_FN u32x2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k)
 constexpr uint32_t kResetStream = 0x80000000u;
 constexpr uint32_t kSpawnStream = 0x40000000u;
 
+ML2048_FN uint32_t stream_key(uint64_t seed, uint32_t tag) { return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ tag; }
+
+ML2048_FN uint32_t block_counter_word(uint64_t index, uint64_t counter)
+{
+    return (uint32_t)counter ^ ((uint32_t)(counter >> 32) * 0x85EBCA6Bu) ^ ((uint32_t)(index >> 32) * 0xC2B2AE35u);
+}
+
 ML2048_FN u32x2 slot_draws(uint64_t index, uint64_t counter, uint64_t seed, uint32_t tag)
 {
-    const uint32_t key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ tag;
-    const uint32_t c1 = (uint32_t)counter ^ ((uint32_t)(counter >> 32) * 0x85EBCA6Bu) ^ ((uint32_t)(index >> 32) * 0xC2B2AE35u);
-    return philox2x32_10((uint32_t)index, c1, key);
+    return philox2x32_10((uint32_t)index, block_counter_word(index, counter), stream_key(seed, tag));
+}
+
+// ... with the stream's round keys precomputed (philox_round_keys)
+ML2048_FN u32x2 slot_draws_keys(uint64_t index, uint64_t counter, const PhiloxKeys &keys)
+{
+    return philox2x32_10_keys((uint32_t)index, block_counter_word(index, counter), keys);
+}
+
+ML2048_FN uint32_t slot_word_keys(uint64_t slot, uint64_t counter, const PhiloxKeys &keys)
+{
+    const u32x2 b = slot_draws_keys(slot >> 1, counter, keys);
+    return (slot & 1ull) ? b.y : b.x;
+}
+
+inline PhiloxKeys philox_round_keys(uint64_t seed, uint32_t tag)  // host side
+{
+    PhiloxKeys keys;
+    uint32_t k = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ tag;  // stream_key
+    for (int i = 0; i < 10; ++i, k += 0x9E3779B9u) keys.k[i] = k;
+    return keys;
 }
 
 // The ONE uniform word a game-step takes from the policy stream (and, in Philox mode, from the spawn stream): a block holds

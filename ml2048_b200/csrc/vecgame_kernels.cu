@@ -585,6 +585,15 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
 constexpr int kPairThreads = ML2048_PAIR_THREADS;
 constexpr int64_t kPairMinGames = 1 << 17;  // below this the batch is latency-bound: more, smaller threads win
 
+// What launch_step works out on the host for the pair kernel and passes as a second kernel parameter: the Philox round keys of
+// the two streams (functions of the seed alone; derived per warp on the uniform datapath they cost ~15 issue slots per warp)
+// and one bit per optional output, so that the kernel tests a flag instead of loading and comparing a 64-bit pointer.
+struct PairConst {
+    PhiloxKeys policy_keys, spawn_keys;
+    uint32_t flags;
+};
+enum : uint32_t { kPairActionsOut = 1u, kPairStats = 2u, kPairAge = 4u, kPairResetIndices = 8u, kPairOddSlotBase = 16u, kPairSched = 32u };
+
 // What a launch draws once: the step's random schedule (scalar arguments, or the pre-drawn entry a CUDA graph replays).
 struct PairEnv {
     int64_t rand_seed;
@@ -593,10 +602,10 @@ struct PairEnv {
     const uint8_t *keys_table;
 };
 
-__device__ __forceinline__ PairEnv pair_env(const ml2048_step_args &a)
+__device__ __forceinline__ PairEnv pair_env(const ml2048_step_args &a, const PairConst &x)
 {
     PairEnv e{a.rand_seed, a.two_mask, a.philox_counter, a.randperm_keys};
-    if (a.sched) {
+    if (x.flags & kPairSched) {
         const int64_t cursor = *a.sched_cursor;
         const ml2048_sched_entry s = a.sched[cursor];
         e.rand_seed = s.rand_seed;
@@ -667,8 +676,8 @@ struct GlobalTables {
 // issue slots per game (parameter load, compare, branch).
 // All 32 lanes of a warp call this together (the fused auto-reset votes); a lane past the end of the batch has live0 = false.
 template <int kRng, bool kReset, bool kRandom, bool kNormalReward, class Tables>
-__device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairEnv &env, const Tables &tab, uint32_t g0, bool live0,
-                                          bool live1, PairLoad &L)
+__device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairConst &x, const PairEnv &env, const Tables &tab, uint32_t g0,
+                                          bool live0, bool live1, PairLoad &L)
 {
     const int64_t rand_seed = env.rand_seed;
     const uint32_t two_mask = env.two_mask;
@@ -713,7 +722,7 @@ __device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairE
             int32_t order = __ldg(a.reset_chunk_base + (group >> 10)) + __ldg(a.reset_rank + group) + __popc(lanes0 & lower) +
                             __popc(lanes1 & lower);
             PrepDraws d{a.rand_base, two_mask, a.prepare_philox_counter, a.randperm};
-            if (a.sched) {
+            if (x.flags & kPairSched) {
                 const ml2048_sched_entry e = a.sched[*a.sched_cursor];
                 d.rand_base = e.rand_base;
                 d.philox_counter = e.philox_counter;
@@ -727,8 +736,8 @@ __device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairE
                     reinterpret_cast<uint4 *>(const_cast<void *>(a.board_in))[g0 + j] = bd[j];
                     reinterpret_cast<uint32_t *>(const_cast<void *>(a.valid_in))[g0 + j] = mask_now[j];
                     a.id[g0 + j] = id_base + order;
-                    if (a.reset_indices && (int64_t)order < a.num_games) a.reset_indices[order] = (int64_t)g0 + j;
-                    if (a.age) a.age[g0 + j] = 0;
+                    if ((x.flags & kPairResetIndices) && (int64_t)order < a.num_games) a.reset_indices[order] = (int64_t)g0 + j;
+                    if (x.flags & kPairAge) a.age[g0 + j] = 0;
                     ss[j] = make_int2(0, 0);
                     order += 1;
                 }
@@ -742,21 +751,21 @@ __device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairE
     const uint64_t slot0 = (uint64_t)(a.slot_base + g0);
     uint32_t policy_word[2] = {0u, 0u}, spawn_word[2] = {0u, 0u};
     if (kRandom) {
-        if ((a.slot_base & 1) == 0) {
-            const u32x2 b = slot_draws(slot0 >> 1, philox_counter, a.philox_seed, 0u);
+        if (!(x.flags & kPairOddSlotBase)) {
+            const u32x2 b = slot_draws_keys(slot0 >> 1, philox_counter, x.policy_keys);
             policy_word[0] = b.x, policy_word[1] = b.y;
         } else {
-            policy_word[0] = slot_word(slot0, philox_counter, a.philox_seed, 0u);
-            policy_word[1] = slot_word(slot0 + 1, philox_counter, a.philox_seed, 0u);
+            policy_word[0] = slot_word_keys(slot0, philox_counter, x.policy_keys);
+            policy_word[1] = slot_word_keys(slot0 + 1, philox_counter, x.policy_keys);
         }
     }
     if (kRng == ML2048_RNG_PHILOX) {
-        if ((a.slot_base & 1) == 0) {
-            const u32x2 b = slot_draws(slot0 >> 1, philox_counter, a.philox_seed, kSpawnStream);
+        if (!(x.flags & kPairOddSlotBase)) {
+            const u32x2 b = slot_draws_keys(slot0 >> 1, philox_counter, x.spawn_keys);
             spawn_word[0] = b.x, spawn_word[1] = b.y;
         } else {
-            spawn_word[0] = slot_word(slot0, philox_counter, a.philox_seed, kSpawnStream);
-            spawn_word[1] = slot_word(slot0 + 1, philox_counter, a.philox_seed, kSpawnStream);
+            spawn_word[0] = slot_word_keys(slot0, philox_counter, x.spawn_keys);
+            spawn_word[1] = slot_word_keys(slot0 + 1, philox_counter, x.spawn_keys);
         }
     }
 
@@ -780,7 +789,7 @@ __device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairE
         const uint32_t row_action = move_board_row(r0, r1, r2, r3, sel_row, f);
         if (kRandom) {
             action = row_action;
-            if (a.actions_out) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
+            if (x.flags & kPairActionsOut) reinterpret_cast<uint8_t *>(a.actions_out)[g] = (uint8_t)action;
         }
         // valid_actions[action] (game_numba.py:718) == "the move changes the board".  The random policy only ever picks a valid
         // direction, so there the move counts exactly when the game has one (mask != 0): no comparison of the boards.  And with
@@ -829,7 +838,7 @@ __device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairE
                 terminated[j] = dead ? 1 : 0;
                 invalid[j] = 0;
             }
-            if (dead && a.stats) {
+            if (dead && (x.flags & kPairStats)) {
                 ml2048_stats *st = a.stats + (blockIdx.x % ML2048_STATS_REPLICAS);
                 const unsigned long long sc = (unsigned long long)score;
                 atomicAdd(&st->max_tile_hist[min(max_cell(r0, r1, r2, r3), 19u)], 1ull);
@@ -856,7 +865,7 @@ __device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairE
 
 // one pair per thread
 template <int kRng, bool kReset, bool kRandom, bool kNormalReward>
-__global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pair_kernel(const ml2048_step_args a)
+__global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pair_kernel(const ml2048_step_args a, const PairConst x)
 {
     const uint32_t n = (uint32_t)a.num_games;  // < 2^31: launch_step
     const uint32_t warp_first = (blockIdx.x * kPairThreads + (threadIdx.x & ~31u)) * 2u;
@@ -867,9 +876,9 @@ __global__ void __launch_bounds__(kPairThreads, ML2048_PAIR_MIN_BLOCKS) step_pai
     // latency the warp cannot hide behind its own work
     PairLoad L;
     pair_load<kReset || kRandom>(a, g0, live0, live1, L);
-    const PairEnv env = pair_env(a);
+    const PairEnv env = pair_env(a, x);
     const GlobalTables tab{reinterpret_cast<const uint4 *>(env.keys_table)};
-    pair_body<kRng, kReset, kRandom, kNormalReward>(a, env, tab, g0, live0, live1, L);
+    pair_body<kRng, kReset, kRandom, kNormalReward>(a, x, env, tab, g0, live0, live1, L);
 }
 
 // A software-pipelined variant of this kernel was built and measured in round 2 and is NOT kept (profiles/pair_loop_experiments_r02.txt): a
@@ -1523,7 +1532,12 @@ int launch_step(const ml2048_step_args &a, cudaStream_t s)
         const bool normal = a.reward_kind == ML2048_REWARD_NORMAL;
         const bool random = a.action_mode == ML2048_ACTIONS_RANDOM_VALID;
         const int variant = (a.reset_rank ? 4 : random ? 2 : 0) + (normal ? 1 : 0);  // the fused auto-reset implies the random policy
-#define ML2048_PAIR_LAUNCH(RESET, RANDOM, NORMAL) step_pair_kernel<kRng, RESET, RANDOM, NORMAL><<<grid, kPairThreads, 0, s>>>(a)
+        PairConst x;
+        x.policy_keys = philox_round_keys(a.philox_seed, 0u);
+        x.spawn_keys = philox_round_keys(a.philox_seed, kSpawnStream);
+        x.flags = (a.actions_out ? kPairActionsOut : 0u) | (a.stats ? kPairStats : 0u) | (a.age ? kPairAge : 0u) |
+                  (a.reset_indices ? kPairResetIndices : 0u) | ((a.slot_base & 1) ? kPairOddSlotBase : 0u) | (a.sched ? kPairSched : 0u);
+#define ML2048_PAIR_LAUNCH(RESET, RANDOM, NORMAL) step_pair_kernel<kRng, RESET, RANDOM, NORMAL><<<grid, kPairThreads, 0, s>>>(a, x)
         switch (variant) {
         case 5: ML2048_PAIR_LAUNCH(true, true, true); break;
         case 4: ML2048_PAIR_LAUNCH(true, true, false); break;
