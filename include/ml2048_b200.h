@@ -334,6 +334,11 @@ ML2048_API int64_t ml2048_autoreset_scratch_ints(int64_t num_games);
 /* host helpers (no GPU work) */
 ML2048_API uint32_t ml2048_two_mask(const float *host_randfloat16, double two_prob);   /* game_numba.py:207 (f32 -> f64 compare) */
 ML2048_API uint32_t ml2048_two_threshold(double two_prob);
+/* cudaMemcpyAsync (kind inferred from the pointers; pinned host memory for a truly asynchronous copy) and cudaStreamSynchronize
+ * for host callers without a CUDA binding of their own: 0 or a cudaError_t. */
+ML2048_API int ml2048_copy_async(void *dst, const void *src, int64_t bytes, void *stream);
+ML2048_API int ml2048_stream_wait(void *stream);
+
 /* Philox mode, the host half of one prepare(): the reference refreshes its spawn tables when `random() >= 0.9`
  * (game_numba.py:622-624) and the 2-vs-4 choice then stays tied to the CELL until the next refresh (:207).  The same two
  * draws from the counter-based stream, keyed by (seed, prepare counter) so that every shard computes identical values:

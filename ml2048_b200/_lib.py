@@ -163,6 +163,8 @@ SYMBOLS = {
     "ml2048_encode_onehot": (C.c_int, [_VP, _VP, _I32, _I64, _VP]),
     "ml2048_valid_actions": (C.c_int, [_VP, _VP, _I64, _VP]),
     "ml2048_max_tile_hist": (C.c_int, [_VP, _VP, _I64, _VP, _VP]),
+    "ml2048_copy_async": (C.c_int, [_VP, _VP, _I64, _VP]),
+    "ml2048_stream_wait": (C.c_int, [_VP]),
     "ml2048_pack_flags": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _VP]),
     "ml2048_unpack_flags": (None, [_VP, _I64, _VP, _VP, _VP, _I32]),
     "ml2048_unpack_flags_sliced": (C.c_int, [_VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _I32]),

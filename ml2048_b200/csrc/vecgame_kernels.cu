@@ -1909,6 +1909,17 @@ int ml2048_gae(const float *v0, const float *v1, const float *reward, const uint
     return launch_status();
 }
 
+// Thin wrappers for host callers that drive the library without a CUDA binding of their own (the NumPy surface of VecGame at
+// the training shape, where a framework-level copy + synchronise costs more host time than the kernels take).
+int ml2048_copy_async(void *dst, const void *src, int64_t bytes, void *stream)
+{
+    if (!dst || !src) return ML2048_E_NULL;
+    if (bytes <= 0) return ML2048_E_SIZE;
+    return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream));
+}
+
+int ml2048_stream_wait(void *stream) { return (int)cudaStreamSynchronize(static_cast<cudaStream_t>(stream)); }
+
 uint32_t ml2048_two_mask(const float *host_randfloat16, double two_prob)
 {
     // game_numba.py:207: `randfloat[idx] < two_prob` with idx the CELL index, f32 promoted to f64

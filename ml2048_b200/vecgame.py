@@ -46,6 +46,11 @@ except AttributeError:  # pragma: no cover - older/newer torch without it
         return torch.cuda.current_stream(index).cuda_stream
 
 
+try:  # torch.cuda.current_device() minus its lazy-init bookkeeping (this runs five times per runner step)
+    _current_device = torch._C._cuda_getDevice
+except AttributeError:  # pragma: no cover
+    _current_device = torch.cuda.current_device
+
 _ONEHOT = {
     None: (_lib.ONEHOT_NONE, None),
     "f32": (_lib.ONEHOT_F32, torch.float32),
@@ -372,7 +377,7 @@ class VecGame:
             self._prev = -1
 
         def __enter__(self):
-            cur = torch.cuda.current_device()
+            cur = _current_device()
             if cur != self._want:
                 self._prev = cur
                 torch.cuda.set_device(self._want)
@@ -467,8 +472,14 @@ class VecGame:
             views["_step"] = views["_step_score"][:, 0]
             views["_score"] = views["_step_score"][:, 1].view(np.float32)
             self._mirror = views
-        self._arena_host.copy_(self._arena, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+            self._arena_copy = (self._arena_host.data_ptr(), self._arena.data_ptr(), self._arena.numel())
+        # (the library's own copy + wait: a torch copy_ + current_stream().synchronize() costs ~15 us of host time per call,
+        # more than the kernels of a 2048-game step take)
+        stream = self._stream()
+        with self._guard:
+            dst, src, nbytes = self._arena_copy
+            _lib.check(self._lib.ml2048_copy_async(dst, src, nbytes, stream), "ml2048_copy_async")
+            _lib.check(self._lib.ml2048_stream_wait(stream), "ml2048_stream_wait")
         self._mirror_epoch = self._state_epoch
         return self._mirror
 
@@ -824,8 +835,11 @@ class VecGame:
             stage = torch.empty((self._size,), dtype=tdtype, pin_memory=True)
             self._host["_actions_stage"] = stage
             self._actions_stage_dev = torch.empty((self._size,), dtype=tdtype, device=self.device)
-        stage.numpy()[...] = actions
-        self._actions_stage_dev.copy_(stage, non_blocking=True)
+            self._host["_actions_stage_np"] = stage.numpy()
+        self._host["_actions_stage_np"][...] = actions
+        with self._guard:
+            _lib.check(self._lib.ml2048_copy_async(self._actions_stage_dev.data_ptr(), stage.data_ptr(), stage.numel() * stage.element_size(),
+                                                   self._stream()), "ml2048_copy_async")
         code = {torch.int64: _lib.ACT_I64, torch.int32: _lib.ACT_I32, torch.uint8: _lib.ACT_U8}[tdtype]
         return self._actions_stage_dev, code
 
