@@ -570,12 +570,16 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
 // part of what it issues there is not game arithmetic: two instructions of address arithmetic for each of nine arrays, the
 // bounds checks, the predicates of the schedule.  A thread that owns TWO ADJACENT games computes every address once (the
 // second game sits at an immediate offset), shares the prologue, and gives the scheduler two independent instruction
-// streams.  Same arithmetic per game as step_kernel (the same board_ops.cuh functions in the same order), same draws (one
-// Philox2x32-10 block per game-step keyed by the global slot), so every array is bit-identical to the one-game-per-thread
-// kernel (tests/test_pair_kernel.py); large batches of the lean configuration are routed here by launch_step.
-// Measured at M = 2^24 (auto-reset fused, random policy / given actions, us per launch; one-game-per-thread kernel: 274.6 / 231):
-// 256 threads x 5 blocks (48 registers) 274.7 / 230.9, x 4 (64) 278.2 / 240.0, x 6 (40) 270.9 / 225.2, x 8 (32, spills) 276.1 / 232.4;
-// 128 threads x 8 (64) 270.4 / 227.9, x 10 (48) 273.0 / 226.8, x 12 (40 registers) 269.4 / 222.2.
+// streams.  Same arithmetic per game as step_kernel (the same board_ops.cuh functions in the same order), same draws (the words
+// of the Philox blocks of the global slot PAIR, which the thread computes once for both of its games), so every array is
+// bit-identical to the one-game-per-thread kernel (tests/test_pair_kernel.py); large batches of the lean configuration are
+// routed here by launch_step.
+// Measured at M = 2^24 (auto-reset fused + random policy / given actions, us per launch):
+//   before the round-2 instruction cuts (one-game-per-thread kernel: 274.6 / 231): 256 threads x 5 blocks (48 registers) 274.7 / 230.9,
+//   x 4 (64) 278.2 / 240.0, x 6 (40) 270.9 / 225.2, x 8 (32, spills) 276.1 / 232.4; 128 threads x 8 (64) 270.4 / 227.9, x 10 (48)
+//   273.0 / 226.8, x 12 (40 registers) 269.4 / 222.2;
+//   after them (profiles/pair_kernel_variants_r02_s.txt): 128 x 12 240.7 / 196.6, 128 x 10 243.9 / 207.1, 128 x 8 247.2 / 207.5,
+//   256 x 6 242.8 / 198.6, 64 x 24 241.4 / 197.4, 128 x 16 (32 registers, spills) 257.0 / 210.4.
 #ifndef ML2048_PAIR_THREADS
 #define ML2048_PAIR_THREADS 128
 #endif
