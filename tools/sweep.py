@@ -29,7 +29,7 @@ def hbm_peak():
 
 def measure(m, rng, onehot, reward, timed=128, warm=256, graph_steps=16):
     out = {}
-    for mode in ("eager", "graph"):
+    for mode in ("eager", "graph", "fused_eager", "fused_graph"):  # fused_*: step_random(auto_reset=True), the reset inside the step kernel
         env = ml2048_b200.VecGame(m, reward, output="torch", rng_mode=rng, onehot=onehot, track_merged=False, sync_free=True)
         env.reset(0)
         for _ in range(warm):
@@ -46,8 +46,16 @@ def measure(m, rng, onehot, reward, timed=128, warm=256, graph_steps=16):
                 env.prepare()
                 env.step_random()
             b.record()
+        elif mode == "fused_eager":
+            for _ in range(8):
+                env.step_random(auto_reset=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(timed):
+                env.step_random(auto_reset=True)
+            b.record()
         else:
-            roll = ml2048_b200.GraphedRollout(env, graph_steps, window=graph_steps * 16)
+            roll = ml2048_b200.GraphedRollout(env, graph_steps, window=graph_steps * 16, auto_reset=mode == "fused_graph")
             roll.replay(1)
             torch.cuda.synchronize()
             a.record()
@@ -75,7 +83,7 @@ def main():
                 if rng == "replay" and onehot in ("bf16", "u8"):
                     continue
                 r = measure(m, rng, onehot, "normal")
-                best = max(r["eager"]["env_steps_per_s"], r["graph"]["env_steps_per_s"])
+                best = max(v["env_steps_per_s"] for v in r.values())
                 pt = {"config": "sweep", "games": m, "rng": rng, "onehot": onehot, "bytes_per_step": BYTES[onehot], **r,
                       "hbm_frac_best": best * BYTES[onehot] / 1e9 / peak}
                 res["points"].append(pt)
