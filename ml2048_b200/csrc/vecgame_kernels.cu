@@ -15,6 +15,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <utility>
+
 #include "../../include/ml2048_b200.h"
 #include "board_ops.cuh"
 
@@ -342,6 +344,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == kOneHotStepThreads      
     }
     bool was_reset = false;
     if (kReset) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // a programmatic dependent of the scan: see autoreset_scan_kernel
         const bool over = live && mask_now == 0u;
         const uint32_t over_lanes = __ballot_sync(0xffffffffu, over);
         if (over) {
@@ -713,6 +716,9 @@ __device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairC
     int2 pair_ss[2] = {make_int2(0, 0), make_int2(0, 0)};
 
     if (kReset) {
+        // (launched as a programmatic dependent of the scan: everything above overlapped it; from here on the kernel reads the
+        // scan's results and writes the `terminated` flags the scan reads.  A no-op when not launched that way.)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         // fused auto-reset (see step_kernel): lane l holds slots 2l and 2l+1 of the warp's 64, i.e. of TWO 32-slot groups
         // of the scan; ranks count the finished games of the lower lanes of the same half-warp, both games of each
         const bool over0 = live0 && mask_now[0] == 0u, over1 = live1 && mask_now[1] == 0u;
@@ -1227,6 +1233,10 @@ __global__ void __launch_bounds__(kScanThreads) autoreset_scan_kernel(const uint
     __shared__ int warp_tot[kScanThreads / 32];
     __shared__ int carry_s;
     __shared__ bool last_s;
+    // Programmatic dependent launch: the fused step that follows may start (load its boards, which the PREVIOUS step wrote and
+    // this kernel does not touch) as soon as every block of this scan is running; it waits (griddepcontrol.wait) before it reads
+    // what the scan writes or writes what the scan reads.
+    asm volatile("griddepcontrol.launch_dependents;");
     const int chunks = (int)gridDim.x;
     const int64_t i = (int64_t)blockIdx.x * kScanThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1466,6 +1476,30 @@ inline int current_device_slot()
     return (dev >= 0 && dev < kMaxDevices) ? dev : -1;
 }
 
+// Launch as a programmatic dependent of the kernel before it on the stream (the auto-reset scan): see autoreset_scan_kernel.
+// ML2048_PDL=0 in the environment keeps the plain stream order (A/B measurements).
+inline bool pdl_enabled()
+{
+    static const bool on = [] { const char *m = getenv("ML2048_PDL"); return !(m && m[0] == '0'); }();
+    return on;
+}
+
+template <typename... Params, typename... Args>
+inline void launch_after_scan(void (*kernel)(Params...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);  // errors surface through launch_status()
+}
+
 template <int kRng, bool kLog, bool kFull, bool kReset>
 int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
 {
@@ -1482,6 +1516,12 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
     const int onehot = a.onehot_out ? a.onehot_dtype : ML2048_ONEHOT_NONE;
     if (onehot < ML2048_ONEHOT_NONE || onehot > ML2048_ONEHOT_U8) return ML2048_E_ENUM;
     clear_stale_error();
+    // with the auto-reset fused in, the step is a programmatic dependent of the scan that precedes it on the stream
+#define ML2048_STEP_LAUNCH(KERNEL, GRID, BLOCK, SMEM)                              \
+    do {                                                                           \
+        if (kReset) launch_after_scan(KERNEL, GRID, BLOCK, SMEM, s, a);            \
+        else KERNEL<<<GRID, BLOCK, SMEM, s>>>(a);                                  \
+    } while (0)
 #if defined(ML2048_ONEHOT_TMA)
 #define ML2048_LAUNCH(OH)                                                                              \
     if (big) {                                                                                         \
@@ -1496,22 +1536,23 @@ int launch_step_onehot(const ml2048_step_args &a, cudaStream_t s)
             if (e != cudaSuccess) return (int)e;                                                       \
             if (dev_slot >= 0) opted_in[dev_slot] = true;                                              \
         }                                                                                              \
-        step_kernel<kRng, kLog, OH, kFull, T, kReset><<<grid_big, T, smem, s>>>(a);                     \
-    } else if (small) step_kernel<kRng, kLog, OH, kFull, S, kReset><<<grid_small, S, 0, s>>>(a);        \
-    else step_kernel<kRng, kLog, OH, kFull, kStepThreads, kReset><<<grid, kStepThreads, 0, s>>>(a)
+        ML2048_STEP_LAUNCH((step_kernel<kRng, kLog, OH, kFull, T, kReset>), grid_big, T, smem);         \
+    } else if (small) ML2048_STEP_LAUNCH((step_kernel<kRng, kLog, OH, kFull, S, kReset>), grid_small, S, 0); \
+    else ML2048_STEP_LAUNCH((step_kernel<kRng, kLog, OH, kFull, kStepThreads, kReset>), grid, kStepThreads, 0)
 #else
 #define ML2048_LAUNCH(OH)                                                                              \
-    if (big) step_kernel<kRng, kLog, OH, kFull, T, kReset><<<grid_big, T, 0, s>>>(a);                   \
-    else if (small) step_kernel<kRng, kLog, OH, kFull, S, kReset><<<grid_small, S, 0, s>>>(a);          \
-    else step_kernel<kRng, kLog, OH, kFull, kStepThreads, kReset><<<grid, kStepThreads, 0, s>>>(a)
+    if (big) ML2048_STEP_LAUNCH((step_kernel<kRng, kLog, OH, kFull, T, kReset>), grid_big, T, 0);       \
+    else if (small) ML2048_STEP_LAUNCH((step_kernel<kRng, kLog, OH, kFull, S, kReset>), grid_small, S, 0); \
+    else ML2048_STEP_LAUNCH((step_kernel<kRng, kLog, OH, kFull, kStepThreads, kReset>), grid, kStepThreads, 0)
 #endif
     switch (onehot) {
-    case ML2048_ONEHOT_NONE: step_kernel<kRng, kLog, ML2048_ONEHOT_NONE, kFull, kStepThreads, kReset><<<grid, kStepThreads, 0, s>>>(a); break;
+    case ML2048_ONEHOT_NONE: ML2048_STEP_LAUNCH((step_kernel<kRng, kLog, ML2048_ONEHOT_NONE, kFull, kStepThreads, kReset>), grid, kStepThreads, 0); break;
     case ML2048_ONEHOT_F32: ML2048_LAUNCH(ML2048_ONEHOT_F32); break;
     case ML2048_ONEHOT_BF16: ML2048_LAUNCH(ML2048_ONEHOT_BF16); break;
     default: ML2048_LAUNCH(ML2048_ONEHOT_U8); break;
     }
 #undef ML2048_LAUNCH
+#undef ML2048_STEP_LAUNCH
     return launch_status();
 }
 
@@ -1545,7 +1586,9 @@ int launch_step(const ml2048_step_args &a, cudaStream_t s)
         x.spawn_keys = philox_round_keys(a.philox_seed, kSpawnStream);
         x.flags = (a.actions_out ? kPairActionsOut : 0u) | (a.stats ? kPairStats : 0u) | (a.age ? kPairAge : 0u) |
                   (a.reset_indices ? kPairResetIndices : 0u) | ((a.slot_base & 1) ? kPairOddSlotBase : 0u) | (a.sched ? kPairSched : 0u);
-#define ML2048_PAIR_LAUNCH(RESET, RANDOM, NORMAL) step_pair_kernel<kRng, RESET, RANDOM, NORMAL><<<grid, kPairThreads, 0, s>>>(a, x)
+#define ML2048_PAIR_LAUNCH(RESET, RANDOM, NORMAL)                                                                 \
+    if (RESET) launch_after_scan(step_pair_kernel<kRng, RESET, RANDOM, NORMAL>, grid, kPairThreads, 0, s, a, x);  \
+    else step_pair_kernel<kRng, RESET, RANDOM, NORMAL><<<grid, kPairThreads, 0, s>>>(a, x)
         switch (variant) {
         case 5: ML2048_PAIR_LAUNCH(true, true, true); break;
         case 4: ML2048_PAIR_LAUNCH(true, true, false); break;
