@@ -658,6 +658,15 @@ __device__ __forceinline__ void pair_load(const ml2048_step_args &a, uint32_t g0
     }
 }
 
+__device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Where a game-step finds its lookup tables: the L1-resident copies in global memory.  (A policy class, so that a kernel
 // with the tables elsewhere can share pair_body: see the software-pipelined experiment below.)
 struct GlobalTables {
@@ -849,13 +858,15 @@ __device__ __forceinline__ void pair_body(const ml2048_step_args &a, const PairC
                 invalid[j] = 0;
             }
             if (dead && (x.flags & kPairStats)) {
+                // (plain reductions: a warp has one or two finished games, so the vote / elect code the compiler wraps around
+                // atomicAdd to aggregate a warp's contributions costs more instructions than it saves transactions)
                 ml2048_stats *st = a.stats + (blockIdx.x % ML2048_STATS_REPLICAS);
                 const unsigned long long sc = (unsigned long long)score;
-                atomicAdd(&st->max_tile_hist[min(max_cell(r0, r1, r2, r3), 19u)], 1ull);
-                atomicAdd(&st->episodes, 1ull);
-                atomicAdd(&st->score_sum, sc);
-                atomicAdd(&st->step_sum, (unsigned long long)nstep);
-                atomicMax(&st->score_max, sc);
+                red_add_u64(&st->max_tile_hist[min(max_cell(r0, r1, r2, r3), 19u)], 1ull);
+                red_add_u64(&st->episodes, 1ull);
+                red_add_u64(&st->score_sum, sc);
+                red_add_u64(&st->step_sum, (unsigned long long)nstep);
+                red_max_u64(&st->score_max, sc);
             }
         } else {
             r0 = bd[j].x, r1 = bd[j].y, r2 = bd[j].z, r3 = bd[j].w;
