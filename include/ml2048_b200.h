@@ -199,7 +199,10 @@ typedef struct {
      * of those games, so every array equals what ml2048_prepare followed by ml2048_step leaves behind.
      * reset_rank / reset_chunk_base / reset_id_base come from ml2048_autoreset_scan (run on the same stream right before);
      * `id` must be writable then.  A game counts as over when its mask is all zero, which is what `terminated` records
-     * (game_numba.py:734-735): the two must agree, as they do for every state the library itself produces. */
+     * (game_numba.py:734-735): the two must agree, as they do for every state the library itself produces.
+     * The launch is a PROGRAMMATIC DEPENDENT of the kernel before it on `stream` (the scan releases its dependents early):
+     * the step reads its boards while the scan still runs and waits before it touches what the scan reads or writes, so
+     * board_in / valid_in / step must be complete before the scan is enqueued -- true for any in-order use of one stream. */
     const int32_t *reset_rank;       /* [ceil(num_games / 32)]: finished games in lower groups of the same 1024-group chunk */
     const int32_t *reset_chunk_base; /* [ceil(groups / 1024)]: finished games in lower chunks */
     const int64_t *reset_id_base;    /* device scalar: id of the first game this step resets */
