@@ -720,13 +720,27 @@ class VecGame:
             self._obs_cache = (got["state"], got["valid_actions"])
             n = int(cnt[0])
             return (self._reset_indices_dev[:n].cpu().numpy() if n else np.zeros((0,), dtype=np.int64),)
+        if self._output == "numpy":
+            # the count and a prefix of the index list that covers the steady state (1.6 % of the games; ~0.9 % finish per
+            # step) behind ONE synchronisation, through pinned memory; the rest follows only if more games were over
+            stage = getattr(self, "_idx_stage", None)
+            if stage is None:
+                cap = int(min(self._size, max(1 << 16, self._size >> 6)))
+                stage = self._idx_stage = torch.empty((cap + 1,), dtype=torch.int64, pin_memory=True)
+                self._idx_stage_np = stage.numpy()
+            cap = stage.numel() - 1
+            stream = self._stream()
+            with self._guard:
+                _lib.check(self._lib.ml2048_copy_async(stage.data_ptr(), self._reset_count_dev.data_ptr(), 8, stream), "ml2048_copy_async")
+                _lib.check(self._lib.ml2048_copy_async(stage.data_ptr() + 8, self._reset_indices_dev.data_ptr(), 8 * cap, stream),
+                           "ml2048_copy_async")
+                _lib.check(self._lib.ml2048_stream_wait(stream), "ml2048_stream_wait")
+            n = int(self._idx_stage_np[0])
+            if n <= cap:
+                return (self._idx_stage_np[1:1 + n].copy(),)
+            return (self._reset_indices_dev[:n].cpu().numpy(),)
         n = int(self._reset_count_dev.item())
-        idx = self._reset_indices_dev[:n]
-        if self._output == "torch":
-            return (idx,)
-        if n == 0:
-            return (np.zeros((0,), dtype=np.int64),)
-        return (idx.cpu().numpy(),)
+        return (self._reset_indices_dev[:n],)
 
     def _prepare_draws(self) -> tuple[int, int]:
         """The host half of one eager prepare() (game_numba.py:622-626): refresh the tables with probability 0.1, draw the

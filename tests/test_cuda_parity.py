@@ -858,3 +858,23 @@ def test_pack_flags_kernel(ml, n):
                 want = want | (inv[off:off + n].to(torch.int32) << 5)
             assert torch.equal(out[off:off + n].to(torch.int32), want), (off, with_term, with_inv)
             assert (out[:off] == 0xAA).all() and (out[off + n:] == 0xAA).all()
+
+
+def test_large_numpy_prepare_returns_the_index_list(ml):
+    """NumPy surface above the batched-host size: prepare() fetches the reset count and a prefix of the ascending index list
+    behind one synchronisation (and the whole list when more games were over than the prefix holds: right after reset())."""
+    m = (1 << 20) + 4096
+    a = _make(ml, m, "normal")                      # NumPy results
+    b = _make(ml, m, "normal", output="torch")
+    a.reset(4)
+    b.reset(4)
+    for t in range(40):
+        (ia,) = a.prepare()
+        (ib,) = b.prepare()
+        assert isinstance(ia, np.ndarray) and ia.dtype == np.int64
+        np.testing.assert_array_equal(ia, ib.cpu().numpy(), err_msg=f"step {t}")
+        if t == 0:
+            assert ia.size == m  # every game starts finished: more than the prefix
+        a.step_random()
+        b.step_random()
+    assert 0 < ia.size < m >> 6
