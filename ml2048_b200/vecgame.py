@@ -1055,6 +1055,12 @@ class VecGame:
 
     _PIPELINE_MIN_GAMES = 1 << 18
     _PIPELINE_CHUNKS = int(os.environ.get("ML2048_PIPELINE_CHUNKS", "8"))  # slices of the H2D / kernel / D2H pipeline
+    # slice sizes ramp up at the front (the D2H stream, which bounds this path, starts after a small slice's H2D + kernel
+    # instead of a full-size one's) and down at the back (less left to expand on the host once the last copy has landed)
+    _PIPELINE_RAMP = os.environ.get("ML2048_PIPELINE_RAMP", "1") != "0"
+    # copy streams the slices alternate between (1, 2, 3 measured 7.35 / 7.41 / 7.42 ms per step at M = 2^24: the copies of one
+    # stream already follow each other without a gap)
+    _PIPELINE_D2H_STREAMS = int(os.environ.get("ML2048_D2H_STREAMS", "1"))
     _PACK_FLAGS = os.environ.get("ML2048_PACK_FLAGS", "1") != "0"  # one byte per game over PCIe for mask + terminated + invalid
     # host threads that expand a slice of packed flags: a share of the host's cores (one process per GPU shares them)
     _UNPACK_THREADS = int(os.environ.get("ML2048_UNPACK_THREADS", "0")) or max(
@@ -1068,6 +1074,27 @@ class VecGame:
         return isinstance(actions, torch.Tensor) and actions.device.type == "cpu" and actions.dtype in (
             torch.int64, torch.int32, torch.uint8, torch.int8)
 
+    def _pipeline_bounds(self, m: int) -> list[int]:
+        """Slice boundaries of the pipelined step (multiples of 256 games, strictly increasing, 0 .. m)."""
+        got = getattr(self, "_pipe_bounds", None)
+        if got is not None and got[-1] == m:
+            return got
+        chunks = max(1, self._PIPELINE_CHUNKS)
+        if self._PIPELINE_RAMP and chunks >= 4:
+            weights = [1, 2, 4] + [8] * (chunks - 2) + [4, 2, 1]
+        else:
+            weights = [1] * chunks
+        total, acc, bounds = sum(weights), 0, [0]
+        for w in weights[:-1]:
+            acc += w
+            b = min(m, (m * acc // total + 255) // 256 * 256)
+            if b > bounds[-1]:
+                bounds.append(b)
+        if bounds[-1] < m:
+            bounds.append(m)
+        self._pipe_bounds = bounds
+        return bounds
+
     def _step_pipelined(self, actions, fetch: tuple) -> VecStepResult:
         if isinstance(actions, np.ndarray):
             actions = torch.from_numpy(np.ascontiguousarray(actions))
@@ -1075,9 +1102,10 @@ class VecGame:
         code = {torch.int64: _lib.ACT_I64, torch.int32: _lib.ACT_I32, torch.uint8: _lib.ACT_U8, torch.int8: _lib.ACT_U8}[actions.dtype]
         m = self._size
         if getattr(self, "_pipe_streams", None) is None:
-            self._pipe_streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+            self._pipe_streams = (torch.cuda.Stream(device=self.device),
+                                  [torch.cuda.Stream(device=self.device) for _ in range(max(1, self._PIPELINE_D2H_STREAMS))])
             self._pipe_actions = {}
-        h2d, d2h = self._pipe_streams
+        h2d, d2h_streams = self._pipe_streams
         dev_actions = self._pipe_actions.get(actions.dtype)
         if dev_actions is None:
             dev_actions = torch.empty((m,), dtype=actions.dtype, device=self.device)
@@ -1123,14 +1151,20 @@ class VecGame:
         a.rand_seed, a.two_mask, a.philox_counter, a.philox_seed = rand_seed, self._two_mask, counter, self._philox_seed
         a.randperm_keys = self._table_ptrs()[1]
         esz = actions.element_size()
-        per = -(-m // self._PIPELINE_CHUNKS)
-        per = (per + 255) // 256 * 256
+        bounds = self._pipeline_bounds(m)
         h2d.wait_stream(main)
-        d2h.wait_stream(main)
+        for d2h in d2h_streams:
+            d2h.wait_stream(main)
         raw_main = main.cuda_stream
+        # tools/e2e_timeline.py: when a list is hung here, every slice appends (lo, hi, event after its kernels, event after its copies)
+        trace = getattr(self, "_pipe_trace", None)
+        if trace is not None:
+            ev_start = torch.cuda.Event(enable_timing=True)
+            ev_start.record(main)
+            trace.append((0, 0, ev_start, ev_start))
         with self._guard:
-            for lo in range(0, m, per):
-                hi = min(m, lo + per)
+            for i, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+                d2h = d2h_streams[i % len(d2h_streams)]  # slices alternate between the copy streams: no gap between their copies
                 with torch.cuda.stream(h2d):
                     dev_actions[lo:hi].copy_(actions[lo:hi], non_blocking=True)
                 main.wait_stream(h2d)
@@ -1158,6 +1192,9 @@ class VecGame:
                     _lib.check(self._lib.ml2048_pack_flags(
                         a.valid_out, a.terminated if "terminated" in fields else None, a.invalid if "invalid" in fields else None,
                         packed_dev.data_ptr() + lo, hi - lo, raw_main), "ml2048_pack_flags")
+                if trace is not None:
+                    ev_kernel = torch.cuda.Event(enable_timing=True)
+                    ev_kernel.record(main)
                 d2h.wait_stream(main)
                 with torch.cuda.stream(d2h):
                     if flag_keys:
@@ -1168,6 +1205,10 @@ class VecGame:
                     for k, t in fields.items():
                         if k not in flag_keys:
                             host[k][lo:hi].copy_(t[lo:hi], non_blocking=True)
+                    if trace is not None:
+                        ev_copied = torch.cuda.Event(enable_timing=True)
+                        ev_copied.record(d2h)
+                        trace.append((lo, hi, ev_kernel, ev_copied))
         self._cur = 1 - cur  # only now: an exception above leaves the ping-pong state where it was
         # bytes this call moves over PCIe towards the host (for callers that account for them: bench.py's e2e)
         self.last_step_d2h_bytes = sum(t.numel() * t.element_size() for k, t in fields.items() if k not in flag_keys) + (m if flag_keys else 0)
@@ -1181,7 +1222,8 @@ class VecGame:
             # behind it are still in flight
             _lib.check(self._lib.ml2048_unpack_flags_sliced(packed_host.data_ptr(), n, lo_arr, hi_arr, ev_arr, ptr["valid_actions"],
                                                             ptr["terminated"], ptr["invalid"], self._UNPACK_THREADS), "ml2048_unpack_flags_sliced")
-        d2h.synchronize()
+        for d2h in d2h_streams:
+            d2h.synchronize()
         res = VecStepResult(self)
         for k in fetch:
             dict.__setitem__(res, k, host[k].numpy())
