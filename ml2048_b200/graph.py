@@ -91,3 +91,7 @@ class GraphedRollout:
             env._check_id_range(self.steps)  # ids are int32: raise before the device counter could wrap
             self.graph.replay()
             env._sched_pos += self.steps
+            # the replay changed the device state behind the host's back: whole-record lookups (`env._data[slot]`) must not be
+            # served from a host snapshot taken before it, nor observations() from a cached copy
+            env._state_epoch += 1
+            env._obs_cache = None

@@ -537,8 +537,13 @@ def test_graph_replay_equals_eager_rollout(ml, m, steps, replays):
     env = _make(ml, m, "improved", output="torch", onehot="f32", sync_free=True)
     env.reset(5)
     roll = ml.GraphedRollout(env, steps, window=steps * 5)
+    before = env._data[3]  # whole-record lookup: takes a host snapshot of the state
     roll.replay(replays)
     torch.cuda.synchronize()
+    # a replay changes the device state: the lookup after it must not be served from the snapshot taken before it
+    after, want = env._data[3], eager._data[3]
+    assert after["step"] == want["step"] and after["id"] == want["id"] and np.array_equal(after["board"], want["board"])
+    assert before["id"] != after["id"] or before["step"] != after["step"]
     assert torch.equal(env.observations()[0], eager.observations()[0])
     assert torch.equal(env.observations()[1], eager.observations()[1])
     assert torch.equal(env._score, eager._score)
