@@ -1054,7 +1054,13 @@ class VecGame:
     # -- host-buffer pipeline -----------------------------------------------------------------------
 
     _PIPELINE_MIN_GAMES = 1 << 18
-    _PIPELINE_CHUNKS = int(os.environ.get("ML2048_PIPELINE_CHUNKS", "8"))  # slices of the H2D / kernel / D2H pipeline
+    # slices of the H2D / kernel / D2H pipeline: 8 at M >= 2^22, fewer below (0 = by batch size) -- a slice costs ~0.1 ms of
+    # host time to enqueue, so slices of fewer than ~2^19 games make the HOST the bound (profiles/e2e_slices_r02.txt:
+    # M = 2^18: 0.30 ms per step with one slice, 0.82 ms with eight; 2^20: 0.71 ms with two, 1.00 ms with eight)
+    _PIPELINE_CHUNKS = int(os.environ.get("ML2048_PIPELINE_CHUNKS", "0"))
+    _PIPELINE_MAX_CHUNKS = 8
+    _PIPELINE_SLICE_GAMES = 1 << 19
+    _PIPELINE_RAMP_MIN_GAMES = 1 << 23
     # slice sizes ramp up at the front (the D2H stream, which bounds this path, starts after a small slice's H2D + kernel
     # instead of a full-size one's) and down at the back (less left to expand on the host once the last copy has landed)
     _PIPELINE_RAMP = os.environ.get("ML2048_PIPELINE_RAMP", "1") != "0"
@@ -1079,8 +1085,8 @@ class VecGame:
         got = getattr(self, "_pipe_bounds", None)
         if got is not None and got[-1] == m:
             return got
-        chunks = max(1, self._PIPELINE_CHUNKS)
-        if self._PIPELINE_RAMP and chunks >= 4:
+        chunks = self._PIPELINE_CHUNKS or min(self._PIPELINE_MAX_CHUNKS, max(1, -(-m // self._PIPELINE_SLICE_GAMES)))
+        if self._PIPELINE_RAMP and chunks >= 4 and m >= self._PIPELINE_RAMP_MIN_GAMES:
             weights = [1, 2, 4] + [8] * (chunks - 2) + [4, 2, 1]
         else:
             weights = [1] * chunks

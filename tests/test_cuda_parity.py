@@ -581,9 +581,13 @@ def test_episode_log_by_game_id(ml, oracle):
         np.testing.assert_array_equal(log[k].cpu().numpy(), want[k], err_msg=k)
 
 
-def test_pipelined_host_step_matches_plain_step(ml, oracle):
+@pytest.mark.parametrize("chunks,ramp_from", [(8, 0), (3, 1 << 30), (0, 1 << 23)])
+def test_pipelined_host_step_matches_plain_step(ml, oracle, monkeypatch, chunks, ramp_from):
     """step(host actions, fetch=...) runs as an H2D / kernel / D2H pipeline over slices of the games; results
-    must equal the one-shot step and the oracle."""
+    must equal the one-shot step and the oracle.  Eight slices ramped up and down (twelve in all, what M >= 2^23 gets),
+    three equal slices, and the default for this size (one slice)."""
+    monkeypatch.setattr(ml.VecGame, "_PIPELINE_CHUNKS", chunks)
+    monkeypatch.setattr(ml.VecGame, "_PIPELINE_RAMP_MIN_GAMES", ramp_from)
     m = (1 << 18) + 777
     ref = oracle.OracleVecGame(m, "improved")
     ref.reset(2)
@@ -610,6 +614,7 @@ def test_pipelined_host_step_matches_plain_step(ml, oracle):
             np.testing.assert_array_equal(r1[k], r0[k], err_msg=f"{k} step {t}")
     oh = env.observations_onehot().cpu().numpy()
     np.testing.assert_array_equal(oh, oracle.onehot(ref.observations()[0]).astype(np.uint8))
+    assert len(env._pipeline_bounds(m)) - 1 == {8: 12, 3: 3, 0: 1}[chunks]
 
 
 def test_reset_midway_and_game_count_survives_reset(ml, oracle):
